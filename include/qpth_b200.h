@@ -1,0 +1,134 @@
+/*
+ * qpth_b200 — C ABI of the B200-native batched differentiable QP solver.
+ *
+ * Drop-in boundary for the hot path of locuslab/qpth (reference @ 528e9f6):
+ *   QPFunction()(Q,p,G,h,A,b) forward + backward
+ *   = qpth/qp.py:23-182 driving qpth/solvers/pdipm/batch.py
+ *     (pre_factor_kkt :375-429, forward :47-207, factor_kkt :435-470,
+ *      solve_kkt :349-372, get_step :210-213).
+ *
+ * The reference has no native code and therefore no FFI; these entry points are
+ * what a binding for that path would call.  Each one names the reference
+ * function it replaces.  All pointers are DEVICE pointers to fp64 data unless a
+ * name ends in `_host`; matrices are row-major and dense; `s*` arguments are
+ * batch strides in ELEMENTS (0 = the tensor is shared by every QP of the batch,
+ * the stride-0 `expand` of qpth/util.py:44-50).  The caller owns every buffer;
+ * the library never allocates user-visible memory, never synchronises the
+ * device (except the *_host convenience call) and reports errors by code.
+ * `stream` is a cudaStream_t passed as void*.
+ *
+ * Semantics: every QP is solved exactly as the reference
+ * solves an nBatch=1 call — the batch-global exit tests (batch.py:127,140) and
+ * the batch-global get_step fill value (batch.py:212) are applied per QP.
+ */
+#ifndef QPTH_B200_H
+#define QPTH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QPB200_OK 0
+#define QPB200_ERR_BAD_ARG 1      /* null pointer / non-positive size */
+#define QPB200_ERR_NO_CONSTRAINTS 2 /* neq == 0 and nineq == 0  (qp.py:89 assert) */
+#define QPB200_ERR_CUDA 3         /* a CUDA runtime call failed: see qpb200_last_cuda_error */
+#define QPB200_ERR_TOO_LARGE 4    /* problem exceeds what the kernels support */
+
+/* Sizes of everything the caller must allocate for one (nz, nineq, neq) shape.
+ * Filled by qpb200_plan_init.  "system" = one distinct (Q,G,A) triple: the
+ * factors are shared by the whole batch when Q, G and A are all un-batched. */
+typedef struct qpb200_plan {
+    int nz, nineq, neq;
+    int neq_pad;            /* neq rounded up to a multiple of 8 (identity-padded rows) */
+    int ms;                 /* neq_pad + nineq: order of the reduced KKT system S */
+    int ldw, lds, rows_s, vl;   /* shared-memory leading dimensions / row counts */
+    int smem_resident;      /* 1: W and the S workspace live in shared memory; 0: global scratch */
+    int threads;            /* CTA size the kernels are launched with */
+    int64_t L_elems;        /* per system: chol(Q), nz*nz doubles (lower, row-major)      [replaces Q_LU]  */
+    int64_t W_elems;        /* per system: [A;G] L^-T, ms*nz doubles                      [whitened G, A]  */
+    int64_t K_elems;        /* per system: block-Cholesky template of S, ms*ms doubles    [replaces S_LU,R] */
+    int64_t setup_scratch_elems;   /* per system, only when smem_resident == 0 (else 0) */
+    int64_t solve_scratch_elems;   /* per QP,     only when smem_resident == 0 (else 0) */
+    int64_t setup_smem_bytes, solve_smem_bytes;
+} qpb200_plan;
+
+int qpb200_version(void);
+const char* qpb200_error_string(int code);
+const char* qpb200_last_cuda_error(void);
+
+/* Fill `plan` for a problem shape. No device work. */
+int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan);
+
+/* pre_factor_kkt (batch.py:375-429) + the SPD check of qp.py:81-85.
+ * nsys systems (1 if Q, G, A are all shared, else nBatch); sQ/sG/sA strides as above.
+ * Writes Lfac (nsys*L_elems), Wfac (nsys*W_elems), Kfac (nsys*K_elems) and
+ * spd_flag[nsys] (0 = SPD, 1 = a pivot of chol(Q) was not positive). */
+int qpb200_pre_factor_kkt(const qpb200_plan* plan, int nsys,
+                          const double* Q, int64_t sQ, const double* G, int64_t sG,
+                          const double* A, int64_t sA,
+                          double* Lfac, double* Wfac, double* Kfac, int* spd_flag,
+                          double* scratch, void* stream);
+
+/* forward (batch.py:47-207): the Mehrotra predictor-corrector loop, one CTA per QP.
+ * sF = 0 if the factors are shared (nsys == 1) else 1.
+ * Outputs: zhat (B,nz), lam (B,nineq), slacks (B,nineq), nus (B,neq) [may be NULL if neq==0],
+ * iters[B] (loop iterations run), best_resid[B] (resids of the returned iterate, batch.py:107).
+ * Exit tests of batch.py:140 are applied per QP: best < eps, mu > 1e32, a NaN iterate, maxIter, and
+ * notImprovedLim consecutive non-improving iterations once best < stall_tol (pass INFINITY for the
+ * reference's literal nBatch=1 behaviour; QPFunction passes 1e-6).
+ * best_tie: the returned iterate is the LATEST one whose resids is below best_tie * min resids (1.0 = the
+ * reference's argmin, batch.py:126-139; QPFunction passes 1.5).
+ * trace (may be NULL): (B, maxIter, 4) doubles receiving pri_resid, dual_resid, mu, resids of every
+ * iteration run — the quantities the reference prints at verbose == 1 (batch.py:115-117). */
+int qpb200_forward(const qpb200_plan* plan, int nbatch,
+                   const double* p, int64_t sp, const double* h, int64_t sh,
+                   const double* b, int64_t sb,
+                   const double* Lfac, const double* Wfac, const double* Kfac, int sF,
+                   double eps, double stall_tol, double best_tie, int notImprovedLim, int maxIter,
+                   double* zhat, double* lam, double* slacks, double* nus,
+                   int* iters, double* best_resid, double* trace, double* scratch, void* stream);
+
+/* QPFunctionFn.backward (qp.py:128-182): one factor_kkt + one solve_kkt per QP and
+ * the gradient outer products.  Any of dQ..db may be NULL (skipped).  For an
+ * input that was passed un-batched, pass mean_X = 1: the gradient is the batch
+ * MEAN (qp.py:159-177) written as one (un-batched) tensor; dxv/dlamv/dnuv are
+ * caller-provided (B,nz)/(B,nineq)/(B,neq) work buffers that receive
+ * dx, dlam, dnu (always written; needed by the mean reduction). */
+int qpb200_backward(const qpb200_plan* plan, int nbatch,
+                    const double* dl_dzhat,
+                    const double* zhat, const double* lam, const double* slacks, const double* nus,
+                    const double* Lfac, const double* Wfac, const double* Kfac, int sF,
+                    double* dQ, int mean_Q, double* dp, int mean_p,
+                    double* dG, int mean_G, double* dh, int mean_h,
+                    double* dA, int mean_A, double* db, int mean_b,
+                    double* dxv, double* dlamv, double* dnuv,
+                    double* scratch, void* stream);
+
+/* factor_kkt + solve_kkt (batch.py:435-470, 349-372) for caller-supplied d and
+ * right-hand sides: one call = LU/Cholesky of R + D^-1 and one reduced KKT solve.
+ * Used by the parity tests of rows a8/a9; not needed by QPFunction itself.
+ * ry/dy may be NULL when neq == 0. All vectors are (B, len). */
+int qpb200_solve_kkt(const qpb200_plan* plan, int nbatch,
+                     const double* d, const double* rx, const double* rs,
+                     const double* rz, const double* ry,
+                     const double* Lfac, const double* Wfac, const double* Kfac, int sF,
+                     double* dx, double* ds, double* dz, double* dy,
+                     double* scratch, void* stream);
+
+/* Whole path on HOST buffers (pageable or pinned): H2D, pre_factor_kkt, forward,
+ * backward, D2H, on `device`; synchronises before returning.  All six inputs
+ * batched (nbatch leading dimension); gradients may be NULL to skip backward. */
+int qpb200_qp_host(int device, int nbatch, int nz, int nineq, int neq,
+                   const double* Q_host, const double* p_host, const double* G_host,
+                   const double* h_host, const double* A_host, const double* b_host,
+                   const double* dl_host, double eps, int notImprovedLim, int maxIter,
+                   double* zhat_host, double* dQ_host, double* dp_host, double* dG_host,
+                   double* dh_host, double* dA_host, double* db_host, int* spd_flag_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

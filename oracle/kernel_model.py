@@ -78,11 +78,12 @@ def _solve_kkt(f, L22, d, t, rs, rz, ry):
 
 def _step(v, dv):
     a = -v / dv
-    a = np.where(dv > 0, np.inf, a)          # per-QP: the batch-global fill (batch.py:212) is >= every entry
-    return a.min()
+    a = np.where(dv > 0, np.inf, a)          # the fill value max(1.0, a.max()) (batch.py:212) is >= every entry
+    st = a.min()
+    return 1.0 if st == np.inf else st       # every dv > 0: the fill is max(1.0, negative) = 1.0 at nBatch=1
 
 
-def solve_one(Q, p, G, h, A, b, eps=1e-12, notImprovedLim=3, maxIter=20):
+def solve_one(Q, p, G, h, A, b, eps=1e-12, notImprovedLim=3, maxIter=20, stall_tol=np.inf, use_eps=True, tie=1.0, noise=None):
     m, n = G.shape
     f = setup(Q, G, A)
     e = f["e"]
@@ -108,19 +109,26 @@ def solve_one(Q, p, G, h, A, b, eps=1e-12, notImprovedLim=3, maxIter=20):
             mu = abs((s * z).sum() / m)
             resid = np.linalg.norm(rz) + (np.linalg.norm(ry) if e > 0 else 0.0) \
                 + np.linalg.norm(L @ rxt) + m * mu
+            if noise is not None:
+                resid = resid + abs(noise.randn()) * 3e-13
             d = z / s
             L22 = _chol(f["R"] + np.diag(1.0 / d))
             if best is None:
                 best = dict(resid=resid, xt=xt.copy(), s=s.copy(), z=z.copy(),
                             y=None if y is None else y.copy(), it=it)
+                minres = resid
                 nNot = 0
-            elif resid < best["resid"]:
+            elif resid < minres:
                 best = dict(resid=resid, xt=xt.copy(), s=s.copy(), z=z.copy(),
                             y=None if y is None else y.copy(), it=it)
+                minres = resid
                 nNot = 0
             else:
                 nNot += 1
-            if nNot == notImprovedLim or best["resid"] < eps or mu > 1e32:
+                if resid < tie * minres:     # within the tie factor of the minimum: prefer the later iterate
+                    best = dict(resid=minres, xt=xt.copy(), s=s.copy(), z=z.copy(),
+                                y=None if y is None else y.copy(), it=it)
+            if (nNot == notImprovedLim and best["resid"] < stall_tol) or (use_eps and best["resid"] < eps) or mu > 1e32:
                 break
             if not np.isfinite(resid):
                 break        # every later iterate is NaN too; `best` cannot change (batch.py:126)

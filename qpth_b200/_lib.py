@@ -1,0 +1,91 @@
+"""ctypes binding of the C ABI in include/qpth_b200.h (libqpth_b200.so, built in-tree by build.py).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is
+present when a solve is requested, the call fails loudly.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqpth_b200.so")
+
+c_double_p = ctypes.c_void_p
+c_int_p = ctypes.c_void_p
+
+
+class Plan(ctypes.Structure):
+    """Mirror of `qpb200_plan` (include/qpth_b200.h)."""
+    _fields_ = [
+        ("nz", ctypes.c_int), ("nineq", ctypes.c_int), ("neq", ctypes.c_int),
+        ("neq_pad", ctypes.c_int), ("ms", ctypes.c_int),
+        ("ldw", ctypes.c_int), ("lds", ctypes.c_int), ("rows_s", ctypes.c_int), ("vl", ctypes.c_int),
+        ("smem_resident", ctypes.c_int), ("threads", ctypes.c_int),
+        ("L_elems", ctypes.c_int64), ("W_elems", ctypes.c_int64), ("K_elems", ctypes.c_int64),
+        ("setup_scratch_elems", ctypes.c_int64), ("solve_scratch_elems", ctypes.c_int64),
+        ("setup_smem_bytes", ctypes.c_int64), ("solve_smem_bytes", ctypes.c_int64),
+    ]
+
+
+# symbol -> (restype, argtypes); also the list tests use to check every declared export exists
+_I, _L, _D, _P = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+SIGNATURES = {
+    "qpb200_version": (_I, []),
+    "qpb200_error_string": (ctypes.c_char_p, [_I]),
+    "qpb200_last_cuda_error": (ctypes.c_char_p, []),
+    "qpb200_plan_init": (_I, [_I, _I, _I, ctypes.POINTER(Plan)]),
+    "qpb200_pre_factor_kkt": (_I, [ctypes.POINTER(Plan), _I, _P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _P, _P]),
+    "qpb200_forward": (_I, [ctypes.POINTER(Plan), _I, _P, _L, _P, _L, _P, _L, _P, _P, _P, _I,
+                            _D, _D, _D, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "qpb200_backward": (_I, [ctypes.POINTER(Plan), _I, _P, _P, _P, _P, _P, _P, _P, _P, _I,
+                             _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P]),
+    "qpb200_solve_kkt": (_I, [ctypes.POINTER(Plan), _I, _P, _P, _P, _P, _P, _P, _P, _P, _I,
+                              _P, _P, _P, _P, _P, _P]),
+    "qpb200_qp_host": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I,
+                            _P, _P, _P, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class QpthB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load libqpth_b200.so (once). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QpthB200Error(
+            "qpth_b200: %s is missing — build it with `python -m qpth_b200.build` "
+            "(there is no CPU fallback)." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        lib = load()
+        msg = lib.qpb200_error_string(rc).decode()
+        if rc == 3:
+            msg += ": " + lib.qpb200_last_cuda_error().decode()
+        raise QpthB200Error("qpth_b200: " + msg)
+
+
+_plans = {}
+
+
+def plan_for(nz, nineq, neq):
+    key = (nz, nineq, neq)
+    if key not in _plans:
+        p = Plan()
+        rc = load().qpb200_plan_init(nz, nineq, neq, ctypes.byref(p))
+        check(rc)
+        _plans[key] = p
+    return _plans[key]

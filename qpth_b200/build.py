@@ -1,0 +1,42 @@
+"""Build libqpth_b200.so in-tree with nvcc for sm_100a (`python -m qpth_b200.build`)."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = [os.path.join(HERE, "csrc", "qp_kernels.cu")]
+DEPS = SRC + [os.path.join(HERE, "csrc", "qp_device.cuh"),
+              os.path.join(os.path.dirname(HERE), "include", "qpth_b200.h")]
+OUT = os.path.join(HERE, "libqpth_b200.so")
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def up_to_date():
+    if not os.path.exists(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    return all(os.path.getmtime(d) <= t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return OUT
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
+           "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-o", OUT] + SRC
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print("built", OUT)

@@ -1,0 +1,937 @@
+// qpth_b200 — sm_100a kernels + C ABI for the batched differentiable QP hot path.
+//
+// Mapping to the reference (locuslab/qpth @ 528e9f6, citations relative to /root/reference):
+//   k_setup     <- pre_factor_kkt            qpth/solvers/pdipm/batch.py:375-429  (+ SPD check qp.py:81-85)
+//   k_forward   <- forward (PDIPM loop)      qpth/solvers/pdipm/batch.py:47-207   (+ get_step :210-213)
+//   k_backward  <- QPFunctionFn.backward     qpth/qp.py:128-182
+//   k_solve_kkt <- factor_kkt + solve_kkt    qpth/solvers/pdipm/batch.py:435-470, 349-372
+//
+// Formulation: with Q = L L^T the variables are whitened, x~ = L^T x, so
+//   W = [A; G] L^-T            (rows 0..ep-1: equality rows, zero-padded to a multiple of 8; then G rows)
+//   S = W W^T + diag(0, 1/d)   (the reduced KKT matrix of solve_kkt; R = G Q^-1 G^T is its lower-right block)
+//   K = block-Cholesky template of S: columns [0,ep) factored once (L11, L21), the trailing block holds
+//       R - L21 L21^T; each factor_kkt call copies K, adds 1/d on the diagonal and finishes the Cholesky.
+// One CTA solves one QP; the whole Newton loop runs inside k_forward with no host round trips.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/qpth_b200.h"
+#include "qp_device.cuh"
+
+using namespace qpb;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxSmem = 232448 - 1024;   // 227 KB opt-in limit per CTA on sm_100, minus static smem slack
+
+struct KDims {
+    int n, m, e, ep, ms;
+    int ldw, lds, rows_s, vl;
+    int lp;          // doubles in the packed lower factor L (rounded up to even)
+};
+
+__host__ __device__ inline int ld_for(int c) {
+    int v = c < 4 ? 4 : c;
+    while ((v & 7) != 4) ++v;
+    return v;
+}
+
+// ---- shared-memory vector slots of the solve / backward kernels (each vl doubles)
+enum Vec {
+    V_PT = 0, V_XT, V_RXT, V_S, V_V, V_RV, V_HW, V_C2, V_W, V_WC, V_DSA, V_DS, V_DXT, V_D,
+    V_BXT, V_BS, V_BV, V_HB, V_DINV, V_DINVL, V_AUG, V_T0, V_T1, V_PART /* 4 slots */, V_COUNT = V_PART + 4
+};
+constexpr int kRedDoubles = 4 * 32;
+
+// vector slots + reduction scratch + 2 mbarriers (16 B)
+__host__ __device__ inline size_t solve_vec_doubles(int vl) { return (size_t)V_COUNT * vl + kRedDoubles + 2; }
+
+// Global-scratch fallback of the K -> S copy (shared-memory mode uses one TMA bulk copy instead).
+__device__ __forceinline__ void copy_K(double* LS, const double* Kg, int total, int tid, int nt) {
+    int i = tid;
+    for (; i + 3 * nt < total; i += 4 * nt) {
+        const double a = Kg[i], b = Kg[i + nt], c = Kg[i + 2 * nt], d = Kg[i + 3 * nt];
+        LS[i] = a; LS[i + nt] = b; LS[i + 2 * nt] = c; LS[i + 3 * nt] = d;
+    }
+    for (; i < total; i += nt) LS[i] = Kg[i];
+}
+
+// get_step (batch.py:210-213) for one QP: min over entries with dv <= 0 of -v/dv;
+// 1.0 when every dv > 0 (the reference's fill value max(1.0, a.max()) at nBatch=1).
+__device__ __forceinline__ double step_candidate(double v, double dv) {
+    return (dv > 0.0) ? INFINITY : (-v / dv);
+}
+
+// Reduced KKT solve with the current factor (solve_kkt, batch.py:349-372), whitened:
+//   aug (in: -h_full restricted to the S system, already forward-substituted) -> w = S^-1 (-h_full)
+// is done by the callers through chol_partial/trsv; this helper finishes dxt = -t - W^T w.
+__device__ __forceinline__ void finish_dxt(const double* W, int ldw, int ms, int n, const double* w,
+                                           const double* t, double* dxt, double* part, int vl,
+                                           int tid, int nt) {
+    const int G = matvec_cols_partial(W, ldw, ms, n, w, part, vl, tid, nt);
+    __syncthreads();
+    for (int c = tid; c < n; c += nt) {
+        double s = 0.0;
+        for (int g = 0; g < G; ++g) s += part[g * vl + c];
+        dxt[c] = -t[c] - s;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_setup: pre_factor_kkt. One CTA per (Q,G,A) system.
+// ---------------------------------------------------------------------------------------------
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads, 1)
+k_setup(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __restrict__ G, int64_t sG,
+        const double* __restrict__ A, int64_t sA, double* __restrict__ Lfac,
+        double* __restrict__ Wfac, double* __restrict__ Kfac, int* __restrict__ spd_flag,
+        double* __restrict__ gscratch, int64_t scratch_per_sys) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int sys = blockIdx.x;
+    const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms;
+    const int ldn = ld_for(n), ldk = ld_for(ms);
+    const int regA = max(n * ldn, ms * ldk);
+    double* base = kSmem ? smem : (gscratch + (int64_t)sys * scratch_per_sys);
+    double* RA = base;                 // Q -> L, later K
+    double* RB = base + regA;          // [Apad; G] -> W   (ms x ldn)
+    double* dinv = kSmem ? (smem + regA + ms * ldn) : smem;   // max(n, ms) doubles
+    __shared__ int s_flag;
+    if (tid == 0) s_flag = 0;
+
+    const double* Qg = Q + (int64_t)sys * sQ;
+    const double* Gg = G + (int64_t)sys * sG;
+    const double* Ag = (e > 0) ? (A + (int64_t)sys * sA) : nullptr;
+    copy_matrix(RA, ldn, Qg, n, n, n, tid, nt);
+    if (e > 0) copy_matrix(RB, ldn, Ag, n, e, n, tid, nt);
+    for (int i = tid; i < (ep - e) * n; i += nt) {   // identity-padded equality rows: W row = 0
+        const int r = e + i / n, c = i % n;
+        RB[r * ldn + c] = 0.0;
+    }
+    copy_matrix(RB + ep * ldn, ldn, Gg, n, m, n, tid, nt);
+    __syncthreads();
+
+    // [Q; Apad; G] -> [L; W]: Cholesky of Q with the constraint rows riding along (W = [A;G] L^-T)
+    chol_partial(RA, ldn, n, 0, n, RB, ldn, ms, dinv, &s_flag, tid, nt);
+
+    double* Lg = Lfac + (int64_t)sys * D.lp;                 // packed lower
+    double* Wg = Wfac + (int64_t)sys * ms * D.ldw;           // row stride ldw (= the SMEM layout)
+    double* Kg = Kfac + (int64_t)sys * ms * D.lds;           // row stride lds (= the SMEM layout)
+    for (int i = tid; i < n * n; i += nt) {
+        const int r = i / n, c = i - r * n;
+        if (c <= r) Lg[(r * (r + 1)) / 2 + c] = RA[r * ldn + c];
+    }
+    if (tid == 0 && (D.lp > n * (n + 1) / 2)) Lg[D.lp - 1] = 0.0;
+    for (int i = tid; i < ms * D.ldw; i += nt) {
+        const int r = i / D.ldw, c = i - r * D.ldw;
+        Wg[i] = (c < n) ? RB[r * ldn + c] : 0.0;
+    }
+    if (tid == 0) spd_flag[sys] = s_flag;
+    __syncthreads();
+
+    // K = W W^T (lower 8x8 tiles, DMMA), dummy equality rows get a unit diagonal
+    {
+        const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+        const int g = lane >> 2, q = lane & 3;
+        const int nts = (ms + 7) >> 3;
+        const int T = nts * (nts + 1) / 2;
+        for (int t = warp; t < T; t += nw) {
+            int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while (ti * (ti + 1) / 2 > t) --ti;
+            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+            const int tj = t - ti * (ti + 1) / 2;
+            const int rr = 8 * ti + g, br = 8 * tj + g;
+            const bool rok = rr < ms, bok = br < ms;
+            const double* pa = RB + (rok ? rr : 0) * ldn;
+            const double* pb = RB + (bok ? br : 0) * ldn;
+            double c0 = 0.0, c1 = 0.0;
+            for (int kk = 0; kk < n; kk += 4) {                 // warp-uniform trip count (mma.sync)
+                const int k = kk + q;
+                const double a = (rok && k < n) ? pa[k] : 0.0, b = (bok && k < n) ? pb[k] : 0.0;
+                dmma884(c0, c1, a, b);
+            }
+            const int cc = 8 * tj + 2 * q;
+            if (rok && cc < ms) RA[rr * ldk + cc] = c0 + ((rr == cc && rr >= e && rr < ep) ? 1.0 : 0.0);
+            if (rok && cc + 1 < ms) RA[rr * ldk + cc + 1] = c1 + ((rr == cc + 1 && rr >= e && rr < ep) ? 1.0 : 0.0);
+        }
+    }
+    __syncthreads();
+    if (ep > 0) chol_partial(RA, ldk, ms, 0, ep, nullptr, 0, 0, dinv, nullptr, tid, nt);
+    for (int i = tid; i < ms * D.lds; i += nt) {
+        const int r = i / D.lds, c = i - r * D.lds;
+        Kg[i] = (c <= r && c < ms) ? RA[r * ldk + c] : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared pieces of k_forward / k_backward / k_solve_kkt
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+    const double* W;    // ms x ldw   (shared memory, or the factor storage itself in global mode)
+    double* LS;         // rows_s x lds: S workspace
+    const double* Lp;   // packed lower chol(Q)
+    double* vec;        // vector slots
+    double* red;        // reduction scratch
+    uint64_t* bar;      // [0]: W + L staged, [1]: K -> LS copies       (shared-memory mode only)
+    const double* Kg;   // K template in global memory (row stride lds)
+    uint32_t kphase;    // parity of the next K copy completion
+    bool kpending;
+};
+
+// K -> LS: one TMA bulk copy per factor_kkt call, issued as soon as the previous factor is dead so that it
+// overlaps the step-length / residual work of the Newton iteration. Call with all threads, after a barrier.
+template <bool kSmem>
+__device__ __forceinline__ void issue_K(const KDims& D, Ctx& C, int tid) {
+    if (kSmem) {
+        if (tid < 32) {
+            fence_proxy_async();
+            if (tid == 0) mbar_expect_tx(C.bar + 1, (uint32_t)(D.ms * D.lds * 8));
+            __syncwarp();
+            bulk_issue_warp(C.LS, C.Kg, (uint32_t)(D.ms * D.lds * 8), C.bar + 1, tid);
+        }
+    }
+    C.kpending = true;
+}
+template <bool kSmem>
+__device__ __forceinline__ void wait_K(const KDims& D, Ctx& C, int tid, int nt) {
+    if (kSmem) {
+        mbar_wait(C.bar + 1, C.kphase);
+        C.kphase ^= 1u;
+    } else {
+        copy_K(C.LS, C.Kg, D.ms * D.lds, tid, nt);
+        __syncthreads();
+    }
+    C.kpending = false;
+}
+
+template <bool kSmem>
+__device__ __forceinline__ Ctx make_ctx(const KDims& D, double* smem, double* gscratch,
+                                        int64_t scratch_per_qp, int qp, const double* Lfac,
+                                        const double* Wfac, const double* Kfac, int sF) {
+    Ctx c;
+    const int64_t sys = sF ? qp : 0;
+    const double* Lg = Lfac + sys * (int64_t)D.lp;
+    const double* Wg = Wfac + sys * (int64_t)D.ms * D.ldw;
+    c.Kg = Kfac + sys * (int64_t)D.ms * D.lds;
+    c.kphase = 0;
+    c.kpending = false;
+    const int tid = threadIdx.x;
+    if (kSmem) {
+        double* W = smem;
+        c.LS = W + D.ms * D.ldw;
+        double* Lp = c.LS + D.rows_s * D.lds;
+        c.vec = Lp + D.lp;
+        c.red = c.vec + (size_t)V_COUNT * D.vl;
+        c.bar = reinterpret_cast<uint64_t*>(c.red + kRedDoubles);
+        c.W = W;
+        c.Lp = Lp;
+        if (tid == 0) {
+            mbar_init(c.bar, 1);
+            mbar_init(c.bar + 1, 1);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const uint32_t wb = (uint32_t)(D.ms * D.ldw * 8), lb = (uint32_t)(D.lp * 8);
+            if (tid == 0) mbar_expect_tx(c.bar, wb + lb);
+            __syncwarp();
+            bulk_issue_warp(W, Wg, wb, c.bar, tid);
+            bulk_issue_warp(Lp, Lg, lb, c.bar, tid);
+        }
+        issue_K<kSmem>(D, c, tid);
+        mbar_wait(c.bar, 0);
+    } else {
+        c.W = Wg;
+        c.Lp = Lg;
+        c.LS = gscratch + (int64_t)qp * scratch_per_qp;
+        c.vec = smem;
+        c.red = c.vec + (size_t)V_COUNT * D.vl;
+        c.bar = nullptr;
+        c.kpending = true;
+    }
+    return c;
+}
+
+#define VEC(i) (C.vec + (size_t)(i) * D.vl)
+
+// factor_kkt + the forward half of solve_kkt: on entry V_AUG holds -h_full (length ms) and V_D holds d.
+// On exit V_W holds w = -S^-1 h_full. Destroys V_AUG, V_T0.
+template <bool kSmem>
+__device__ __forceinline__ void factor_and_solve(const KDims& D, Ctx& C, int tid, int nt) {
+    double* aug = VEC(V_AUG);
+    wait_K<kSmem>(D, C, tid, nt);
+    for (int i = D.ep + tid; i < D.ms; i += nt) C.LS[i * D.lds + i] += 1.0 / VEC(V_D)[i];
+    __syncthreads();
+    const FullIdx at{D.lds};
+    if (D.ep > 0) {
+        // equality block: forward-substitute the first ep entries with the pre-factored L11 / L21
+        trsv_fwd(C.LS, at, D.ms, 0, D.ep, VEC(V_DINV), aug, VEC(V_T0), tid, nt);
+        for (int i = tid; i < D.ep; i += nt) aug[i] = VEC(V_T0)[i];
+        __syncthreads();
+    }
+    chol_partial(C.LS, D.lds, D.ms, D.ep, D.ms, aug, 0, 1, VEC(V_DINV), nullptr, tid, nt);
+    trsv_bwd(C.LS, at, D.ms, VEC(V_DINV), aug, VEC(V_W), tid, nt);
+}
+
+// Solve with the factor already in LS: rhs in V_T1 (destroyed) -> result in `out`.
+__device__ __forceinline__ void solve_with_factor(const KDims& D, const Ctx& C, double* out, int tid,
+                                                  int nt) {
+    const FullIdx at{D.lds};
+    trsv_fwd(C.LS, at, D.ms, 0, D.ms, VEC(V_DINV), VEC(V_T1), VEC(V_T0), tid, nt);
+    trsv_bwd(C.LS, at, D.ms, VEC(V_DINV), VEC(V_T0), out, tid, nt);
+}
+
+// x~ = L^-1 x: V_T1 (destroyed) -> dst.  x = L^-T x~: u (destroyed) -> out.
+__device__ __forceinline__ void whiten(const KDims& D, const Ctx& C, double* dst, int tid, int nt) {
+    trsv_fwd(C.Lp, PackedIdx{}, D.n, 0, D.n, VEC(V_DINVL), VEC(V_T1), dst, tid, nt);
+}
+__device__ __forceinline__ void unwhiten(const KDims& D, const Ctx& C, double* u, double* out, int tid,
+                                         int nt) {
+    trsv_bwd(C.Lp, PackedIdx{}, D.n, VEC(V_DINVL), u, out, tid, nt);
+}
+// common prologue: reciprocal diagonals of L and of the pre-factored equality block
+__device__ __forceinline__ void load_dinvs(const KDims& D, const Ctx& C, int tid, int nt) {
+    for (int i = tid; i < D.n; i += nt) VEC(V_DINVL)[i] = 1.0 / C.Lp[(i * (i + 1)) / 2 + i];
+    for (int i = tid; i < D.ep; i += nt) VEC(V_DINV)[i] = 1.0 / C.Kg[(int64_t)i * D.lds + i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_forward: the PDIPM loop (batch.py:47-207), per-QP semantics.
+// ---------------------------------------------------------------------------------------------
+template <bool kSmem>
+__global__ void __launch_bounds__(kThreads, 1)
+k_forward(KDims D, const double* __restrict__ p, int64_t sp, const double* __restrict__ h,
+          int64_t sh, const double* __restrict__ b, int64_t sb, const double* __restrict__ Lfac,
+          const double* __restrict__ Wfac, const double* __restrict__ Kfac, int sF, double eps,
+          double stall_tol, double best_tie, int notImprovedLim, int maxIter, double* __restrict__ zhat, double* __restrict__ lam,
+          double* __restrict__ slacks, double* __restrict__ nus, int* __restrict__ iters_out,
+          double* __restrict__ resid_out, double* __restrict__ trace, double* __restrict__ gscratch,
+          int64_t scratch_per_qp) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int qp = blockIdx.x;
+    const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms;
+    Ctx C = make_ctx<kSmem>(D, smem, gscratch, scratch_per_qp, qp, Lfac, Wfac, Kfac, sF);
+
+    double* pt = VEC(V_PT); double* xt = VEC(V_XT); double* rxt = VEC(V_RXT);
+    double* s = VEC(V_S); double* v = VEC(V_V); double* rv = VEC(V_RV); double* hW = VEC(V_HW);
+    double* c2 = VEC(V_C2); double* w = VEC(V_W); double* wc = VEC(V_WC); double* dsa = VEC(V_DSA);
+    double* ds = VEC(V_DS); double* dxt = VEC(V_DXT); double* d = VEC(V_D); double* hb = VEC(V_HB);
+    double* aug = VEC(V_AUG); double* t1 = VEC(V_T1); double* part = VEC(V_PART);
+
+    // ---- load per-QP vectors; hb = [b; 0; h]
+    const double* pg = p + (int64_t)qp * sp;
+    const double* hg = h + (int64_t)qp * sh;
+    const double* bg = (e > 0) ? (b + (int64_t)qp * sb) : nullptr;
+    for (int i = tid; i < n; i += nt) t1[i] = pg[i];
+    for (int i = tid; i < ms; i += nt) {
+        double val = 0.0;
+        if (i < e) val = bg[i];
+        else if (i >= ep) val = hg[i - ep];
+        hb[i] = val;
+        d[i] = 1.0;
+        s[i] = 0.0;
+    }
+    load_dinvs(D, C, tid, nt);
+    __syncthreads();
+    whiten(D, C, pt, tid, nt);                                  // p~ = L^-1 p
+
+    // ---- initial point: solve_kkt(p, 0, -h, -b) with d = 1   (batch.py:61-67)
+    matvec_rows<false>(C.W, D.ldw, ms, n, pt, nullptr, hW, nullptr, tid, nt);
+    __syncthreads();
+    for (int i = tid; i < ms; i += nt) aug[i] = -(hW[i] + hb[i]);
+    __syncthreads();
+    factor_and_solve<kSmem>(D, C, tid, nt);
+    issue_K<kSmem>(D, C, tid);
+    finish_dxt(C.W, D.ldw, ms, n, w, pt, xt, part, D.vl, tid, nt);   // x~ = -p~ - W^T w
+    {
+        double mn[2] = {INFINITY, INFINITY};
+        for (int i = ep + tid; i < ms; i += nt) {
+            v[i] = w[i];
+            s[i] = -w[i];
+            mn[0] = fmin(mn[0], -w[i]);
+            mn[1] = fmin(mn[1], w[i]);
+        }
+        for (int i = tid; i < ep; i += nt) v[i] = w[i];
+        block_reduce<2, true>(mn, C.red, tid, nt);
+        // make slacks and inequality duals >= 1 (batch.py:77-87)
+        for (int i = ep + tid; i < ms; i += nt) {
+            if (mn[0] < 0.0) s[i] -= mn[0] - 1.0;
+            if (mn[1] < 0.0) v[i] -= mn[1] - 1.0;
+        }
+        __syncthreads();
+    }
+
+    double best = 0.0, ret_resid = 0.0;
+    int nNot = 0, it = 0, iters_run = 0;
+    const double dm = (double)m;
+    for (it = 0; it < maxIter; ++it) {
+        iters_run = it + 1;
+        // ---- residuals (batch.py:94-107)
+        {
+            const int G = matvec_cols_partial(C.W, D.ldw, ms, n, v, part, D.vl, tid, nt);
+            __syncthreads();
+            for (int c = tid; c < n; c += nt) {
+                double sum = 0.0;
+                for (int g = 0; g < G; ++g) sum += part[g * D.vl + c];
+                rxt[c] = xt[c] + pt[c] + sum;                   // L^-1 (Qx + p + G^T z + A^T y)
+            }
+            __syncthreads();
+        }
+        matvec_rows<true>(C.W, D.ldw, ms, n, xt, rxt, c2, hW, tid, nt);
+        __syncthreads();
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};                   // |ry|^2, |rz|^2, |L r~x|^2, s.z
+        for (int i = tid; i < ms; i += nt) {
+            const double r = c2[i] - hb[i] + ((i >= ep) ? s[i] : 0.0);   // [Ax - b; Gx + s - h]
+            rv[i] = r;
+            if (i < ep) acc[0] = fma(r, r, acc[0]);
+            else { acc[1] = fma(r, r, acc[1]); acc[3] = fma(s[i], v[i], acc[3]); }
+        }
+        acc[2] = tri_norm2_partial(C.Lp, n, rxt, tid, nt);      // || L r~x ||^2 = ||Qx + p + G^T z + A^T y||^2
+        block_reduce<4, false>(acc, C.red, tid, nt);
+        const double mu = fabs(acc[3] / dm);
+        const double resid = sqrt(acc[1]) + sqrt(acc[0]) + sqrt(acc[2]) + dm * mu;
+        if (trace != nullptr && tid == 0) {                     // what verbose=1 prints (batch.py:115-117)
+            double* tr = trace + ((int64_t)qp * maxIter + it) * 4;
+            tr[0] = sqrt(acc[1]) + sqrt(acc[0]); tr[1] = sqrt(acc[2]); tr[2] = mu; tr[3] = resid;
+        }
+        // ---- best-iterate tracking and exit tests (batch.py:118-143), per QP
+        const bool improved = (it == 0) || (resid < best);      // strict, as the reference (NaN never improves)
+        if (improved) { best = resid; nNot = 0; } else { ++nNot; }
+        // Returned iterate: the reference keeps argmin resids. At the rounding floor consecutive iterates tie
+        // to within noise while mu keeps shrinking 1000x per step; among iterates within best_tie of the
+        // minimum the LATEST is kept, so the backward pass's 1e-8 clamps (qp.py:148) see converged duals.
+        if (improved || resid < best_tie * best) {
+            ret_resid = resid;
+            for (int i = tid; i < n; i += nt) VEC(V_BXT)[i] = xt[i];
+            for (int i = tid; i < ms; i += nt) { VEC(V_BS)[i] = s[i]; VEC(V_BV)[i] = v[i]; }
+        }
+        // batch.py:140 per QP; the not-improved rule only fires once the QP is in its converged regime
+        // (best < stall_tol): in a batch the reference keeps iterating while any other QP improves.
+        if ((nNot == notImprovedLim && best < stall_tol) || best < eps || mu > 1e32) break;
+        if (!(resid == resid) || isinf(resid)) break;           // every later iterate is NaN too
+        // ---- factor_kkt with d = z/s and the affine right-hand side (batch.py:109-113,150)
+        for (int i = tid; i < ms; i += nt) {
+            double hfull = hW[i] - rv[i];
+            if (i >= ep) {
+                const double di = v[i] / s[i];
+                d[i] = di;
+                hfull += v[i] / di;                             // rs/d with rs = z
+            }
+            aug[i] = -hfull;
+        }
+        __syncthreads();
+        factor_and_solve<kSmem>(D, C, tid, nt);                 // w = [dy_aff; dz_aff]
+        // ---- affine step length and sigma (batch.py:160-168)
+        double mn[2] = {INFINITY, INFINITY};
+        for (int i = ep + tid; i < ms; i += nt) {
+            const double dz = w[i];
+            const double dsi = (-v[i] - dz) / d[i];
+            dsa[i] = dsi;
+            mn[0] = fmin(mn[0], step_candidate(v[i], dz));
+            mn[1] = fmin(mn[1], step_candidate(s[i], dsi));
+        }
+        block_reduce<2, true>(mn, C.red, tid, nt);
+        {
+            const double stz = isinf(mn[0]) && mn[0] > 0 ? 1.0 : mn[0];
+            const double sts = isinf(mn[1]) && mn[1] > 0 ? 1.0 : mn[1];
+            const double alpha = fmin(fmin(stz, sts), 1.0);
+            double sm[2] = {0.0, 0.0};
+            for (int i = ep + tid; i < ms; i += nt) {
+                sm[0] = fma(s[i] + alpha * dsa[i], v[i] + alpha * w[i], sm[0]);
+                sm[1] = fma(s[i], v[i], sm[1]);
+            }
+            block_reduce<2, false>(sm, C.red, tid, nt);
+            const double sr = sm[0] / sm[1];
+            const double sig = sr * sr * sr;
+            // ---- corrector (batch.py:170-181): rx = rz = ry = 0, rs = (-mu*sig + ds_aff*dz_aff)/s
+            for (int i = tid; i < ms; i += nt) {
+                double rhs = 0.0;
+                if (i >= ep) {
+                    const double rsc = (-mu * sig + dsa[i] * w[i]) / s[i];
+                    ds[i] = rsc;                                 // keep rs_c for ds_cor below
+                    rhs = -(rsc / d[i]);
+                }
+                t1[i] = rhs;
+            }
+            __syncthreads();
+        }
+        solve_with_factor(D, C, wc, tid, nt);                   // wc = [dy_cor; dz_cor]
+        issue_K<kSmem>(D, C, tid);                              // next factor_kkt's copy of K overlaps the rest
+        // ---- combined direction, step length, update (batch.py:185-203)
+        mn[0] = INFINITY; mn[1] = INFINITY;
+        for (int i = tid; i < ms; i += nt) {
+            const double dv = w[i] + wc[i];
+            w[i] = dv;
+            if (i >= ep) {
+                const double dsc = (-ds[i] - wc[i]) / d[i];
+                const double dsi = dsa[i] + dsc;
+                ds[i] = dsi;
+                mn[0] = fmin(mn[0], step_candidate(v[i], dv));
+                mn[1] = fmin(mn[1], step_candidate(s[i], dsi));
+            }
+        }
+        __syncthreads();
+        finish_dxt(C.W, D.ldw, ms, n, w, rxt, dxt, part, D.vl, tid, nt);   // dx~ = -r~x - W^T dv
+        block_reduce<2, true>(mn, C.red, tid, nt);
+        {
+            const double stz = isinf(mn[0]) && mn[0] > 0 ? 1.0 : mn[0];
+            const double sts = isinf(mn[1]) && mn[1] > 0 ? 1.0 : mn[1];
+            const double alpha = fmin(0.999 * fmin(stz, sts), 1.0);
+            for (int i = tid; i < n; i += nt) xt[i] = fma(alpha, dxt[i], xt[i]);
+            for (int i = tid; i < ms; i += nt) {
+                v[i] = fma(alpha, w[i], v[i]);
+                if (i >= ep) s[i] = fma(alpha, ds[i], s[i]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- outputs: x = L^-T x~_best, y, z, s of the best iterate (batch.py:205-207)
+    __syncthreads();
+    unwhiten(D, C, VEC(V_BXT), VEC(V_T0), tid, nt);
+    if (kSmem && C.kpending) wait_K<kSmem>(D, C, tid, nt);      // drain the in-flight copy before exit
+    for (int i = tid; i < n; i += nt) zhat[(int64_t)qp * n + i] = VEC(V_T0)[i];
+    for (int i = tid; i < m; i += nt) {
+        lam[(int64_t)qp * m + i] = VEC(V_BV)[ep + i];
+        slacks[(int64_t)qp * m + i] = VEC(V_BS)[ep + i];
+    }
+    if (e > 0 && nus != nullptr)
+        for (int i = tid; i < e; i += nt) nus[(int64_t)qp * e + i] = VEC(V_BV)[i];
+    if (tid == 0) {
+        iters_out[qp] = iters_run;
+        resid_out[qp] = ret_resid;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_solve_kkt: factor_kkt + solve_kkt for caller-supplied d and right-hand sides.
+// kBackward: the backward pass of QPFunction (qp.py:128-182): d from clamped lam/slacks, rx = dl,
+// other right-hand sides zero, fused gradient outer products for batched inputs.
+// ---------------------------------------------------------------------------------------------
+struct BwdOut {
+    double* dQ; double* dp; double* dG; double* dh; double* dA; double* db;
+    int mQ, mp, mG, mh, mA, mb;      // 1 = mean-reduced elsewhere (skip per-QP write)
+};
+
+template <bool kSmem, bool kBackward>
+__global__ void __launch_bounds__(kThreads, 1)
+k_solve_kkt(KDims D, const double* __restrict__ d_in, const double* __restrict__ rx_in,
+            const double* __restrict__ rs_in, const double* __restrict__ rz_in,
+            const double* __restrict__ ry_in, const double* __restrict__ zhat,
+            const double* __restrict__ lam, const double* __restrict__ slacks,
+            const double* __restrict__ nus, const double* __restrict__ Lfac,
+            const double* __restrict__ Wfac, const double* __restrict__ Kfac, int sF,
+            double* __restrict__ dx_out, double* __restrict__ ds_out, double* __restrict__ dz_out,
+            double* __restrict__ dy_out, BwdOut O, double* __restrict__ gscratch,
+            int64_t scratch_per_qp) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int qp = blockIdx.x;
+    const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms;
+    Ctx C = make_ctx<kSmem>(D, smem, gscratch, scratch_per_qp, qp, Lfac, Wfac, Kfac, sF);
+    double* t = VEC(V_PT); double* d = VEC(V_D); double* hW = VEC(V_HW); double* aug = VEC(V_AUG);
+    double* w = VEC(V_W); double* t1 = VEC(V_T1); double* dxt = VEC(V_DXT); double* part = VEC(V_PART);
+    double* rsv = VEC(V_S);
+
+    for (int i = tid; i < n; i += nt) t1[i] = rx_in[(int64_t)qp * n + i];
+    for (int i = tid; i < ms; i += nt) {
+        double di = 1.0, extra = 0.0, rsi = 0.0;
+        if (i >= ep) {
+            const int j = i - ep;
+            if (kBackward) {
+                di = fmax(lam[(int64_t)qp * m + j], 1e-8) / fmax(slacks[(int64_t)qp * m + j], 1e-8);   // qp.py:148
+            } else {
+                di = d_in[(int64_t)qp * m + j];
+                rsi = rs_in[(int64_t)qp * m + j];
+                extra = rsi / di - rz_in[(int64_t)qp * m + j];
+            }
+        } else if (!kBackward && i < e) {
+            extra = -ry_in[(int64_t)qp * e + i];
+        }
+        d[i] = di;
+        rsv[i] = rsi;
+        hW[i] = extra;                                          // [-ry; rs/d - rz]
+    }
+    load_dinvs(D, C, tid, nt);
+    __syncthreads();
+    whiten(D, C, t, tid, nt);                                   // t = L^-1 rx
+    matvec_rows<false>(C.W, D.ldw, ms, n, t, nullptr, VEC(V_C2), nullptr, tid, nt);
+    __syncthreads();
+    for (int i = tid; i < ms; i += nt) aug[i] = -(VEC(V_C2)[i] + hW[i]);
+    __syncthreads();
+    factor_and_solve<kSmem>(D, C, tid, nt);                     // w = [dy; dz]
+    finish_dxt(C.W, D.ldw, ms, n, w, t, dxt, part, D.vl, tid, nt);
+    unwhiten(D, C, dxt, VEC(V_XT), tid, nt);                    // dx = L^-T dx~
+    const double* dx = VEC(V_XT);
+    for (int i = tid; i < n; i += nt) dx_out[(int64_t)qp * n + i] = dx[i];
+    for (int i = tid; i < m; i += nt) {
+        dz_out[(int64_t)qp * m + i] = w[ep + i];
+        if (!kBackward) ds_out[(int64_t)qp * m + i] = (-rsv[ep + i] - w[ep + i]) / d[ep + i];
+    }
+    if (e > 0 && dy_out != nullptr)
+        for (int i = tid; i < e; i += nt) dy_out[(int64_t)qp * e + i] = w[i];
+    if (!kBackward) return;
+
+    // ---- gradients for batched inputs (qp.py:157-176); mean-reduced ones are done by k_mean_*
+    double* zs = VEC(V_BXT); double* ls = VEC(V_BV);
+    for (int i = tid; i < n; i += nt) zs[i] = zhat[(int64_t)qp * n + i];
+    for (int i = tid; i < m; i += nt) ls[ep + i] = lam[(int64_t)qp * m + i];
+    for (int i = tid; i < e; i += nt) ls[i] = nus[(int64_t)qp * e + i];
+    __syncthreads();
+    if (O.dp && !O.mp) for (int i = tid; i < n; i += nt) O.dp[(int64_t)qp * n + i] = dx[i];
+    if (O.dh && !O.mh) for (int i = tid; i < m; i += nt) O.dh[(int64_t)qp * m + i] = -w[ep + i];
+    if (O.db && !O.mb && e > 0) for (int i = tid; i < e; i += nt) O.db[(int64_t)qp * e + i] = -w[i];
+    if (O.dQ && !O.mQ) {
+        double* o = O.dQ + (int64_t)qp * n * n;
+        for (int i = tid; i < n * n; i += nt) {
+            const int r = i / n, c = i - r * n;
+            o[i] = 0.5 * (dx[r] * zs[c] + zs[r] * dx[c]);
+        }
+    }
+    if (O.dG && !O.mG) {
+        double* o = O.dG + (int64_t)qp * m * n;
+        for (int i = tid; i < m * n; i += nt) {
+            const int r = i / n, c = i - r * n;
+            o[i] = w[ep + r] * zs[c] + ls[ep + r] * dx[c];
+        }
+    }
+    if (O.dA && !O.mA && e > 0) {
+        double* o = O.dA + (int64_t)qp * e * n;
+        for (int i = tid; i < e * n; i += nt) {
+            const int r = i / n, c = i - r * n;
+            o[i] = w[r] * zs[c] + ls[r] * dx[c];
+        }
+    }
+}
+
+// Batch-mean gradients for un-batched inputs (qp.py:159-177): out[r][c] = (1/B) sum_b (u_b[r] x_b[c] + y_b[r] v_b[c]) * scale
+__global__ void k_mean_outer(int B, int rows, int cols, const double* __restrict__ u,
+                             const double* __restrict__ x, const double* __restrict__ y,
+                             const double* __restrict__ v, double scale, double* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const int r = idx / cols, c = idx - r * cols;
+    double s = 0.0;
+    for (int bidx = 0; bidx < B; ++bidx)
+        s += u[(int64_t)bidx * rows + r] * x[(int64_t)bidx * cols + c] +
+             y[(int64_t)bidx * rows + r] * v[(int64_t)bidx * cols + c];
+    out[idx] = s * scale / (double)B;
+}
+__global__ void k_mean_vec(int B, int len, const double* __restrict__ u, double scale,
+                           double* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= len) return;
+    double s = 0.0;
+    for (int bidx = 0; bidx < B; ++bidx) s += u[(int64_t)bidx * len + idx];
+    out[idx] = s * scale / (double)B;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t err, const char* what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(err));
+    return QPB200_ERR_CUDA;
+}
+#define CK(call)                                          \
+    do {                                                  \
+        cudaError_t _e = (call);                          \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+    } while (0)
+
+KDims dims_of(const qpb200_plan* p) {
+    KDims D;
+    D.n = p->nz; D.m = p->nineq; D.e = p->neq; D.ep = p->neq_pad; D.ms = p->ms;
+    D.ldw = p->ldw; D.lds = p->lds; D.rows_s = p->rows_s; D.vl = p->vl;
+    D.lp = (int)p->L_elems;
+    return D;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return QPB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qpb200_version(void) { return 100; }
+
+const char* qpb200_error_string(int code) {
+    switch (code) {
+        case QPB200_OK: return "ok";
+        case QPB200_ERR_BAD_ARG: return "bad argument";
+        case QPB200_ERR_NO_CONSTRAINTS: return "neq == 0 and nineq == 0";
+        case QPB200_ERR_CUDA: return "CUDA runtime error";
+        case QPB200_ERR_TOO_LARGE: return "problem too large";
+        default: return "unknown error";
+    }
+}
+
+const char* qpb200_last_cuda_error(void) { return g_cuda_err; }
+
+int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
+    if (plan == nullptr || nz <= 0 || nineq < 0 || neq < 0) return QPB200_ERR_BAD_ARG;
+    if (nineq == 0 && neq == 0) return QPB200_ERR_NO_CONSTRAINTS;
+    if (nz > 4096 || nineq > 4096 || neq > 4096) return QPB200_ERR_TOO_LARGE;
+    memset(plan, 0, sizeof(*plan));
+    plan->nz = nz; plan->nineq = nineq; plan->neq = neq;
+    plan->neq_pad = (neq + 7) & ~7;
+    plan->ms = plan->neq_pad + nineq;
+    const int ms = plan->ms;
+    plan->ldw = ld_for(nz);
+    plan->lds = ld_for(nz > ms ? nz : ms);
+    plan->rows_s = (nz > ms + 1) ? nz : (ms + 1);
+    int vl = (nz > ms ? nz : ms) + 8;
+    plan->vl = (vl + 7) & ~7;
+    plan->threads = kThreads;
+    plan->L_elems = (((int64_t)nz * (nz + 1)) / 2 + 1) & ~(int64_t)1;   // packed lower, even count
+    plan->W_elems = (int64_t)ms * plan->ldw;
+    plan->K_elems = (int64_t)ms * plan->lds;
+    const int ldn = ld_for(nz), ldk = ld_for(ms);
+    const int64_t regA = (int64_t)nz * ldn > (int64_t)ms * ldk ? (int64_t)nz * ldn : (int64_t)ms * ldk;
+    const int64_t setup_mat = regA + (int64_t)ms * ldn;
+    const int64_t setup_vec = (nz > ms ? nz : ms) + 8;
+    const int64_t solve_mat_s = (int64_t)ms * plan->ldw + (int64_t)plan->rows_s * plan->lds + plan->L_elems;
+    const int64_t solve_mat = (int64_t)plan->rows_s * plan->lds;     // global mode: only the S workspace
+    const int64_t solve_vec = (int64_t)solve_vec_doubles(plan->vl);
+    const bool fits = (solve_mat_s + solve_vec) * 8 <= kMaxSmem && (setup_mat + setup_vec) * 8 <= kMaxSmem;
+    plan->smem_resident = fits ? 1 : 0;
+    if (fits) {
+        plan->setup_smem_bytes = (setup_mat + setup_vec) * 8;
+        plan->solve_smem_bytes = (solve_mat_s + solve_vec) * 8;
+        plan->setup_scratch_elems = 0;
+        plan->solve_scratch_elems = 0;
+    } else {
+        plan->setup_smem_bytes = setup_vec * 8;
+        plan->solve_smem_bytes = solve_vec * 8;
+        if (plan->solve_smem_bytes > kMaxSmem) return QPB200_ERR_TOO_LARGE;
+        plan->setup_scratch_elems = setup_mat;
+        plan->solve_scratch_elems = solve_mat;
+    }
+    return QPB200_OK;
+}
+
+int qpb200_pre_factor_kkt(const qpb200_plan* plan, int nsys, const double* Q, int64_t sQ,
+                          const double* G, int64_t sG, const double* A, int64_t sA, double* Lfac,
+                          double* Wfac, double* Kfac, int* spd_flag, double* scratch, void* stream) {
+    if (!plan || nsys <= 0 || !Q || !Lfac || !Wfac || !Kfac || !spd_flag) return QPB200_ERR_BAD_ARG;
+    if (plan->nineq > 0 && !G) return QPB200_ERR_BAD_ARG;
+    if (plan->neq > 0 && !A) return QPB200_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    KDims D = dims_of(plan);
+    if (plan->smem_resident) {
+        int rc = set_smem(k_setup<true>, plan->setup_smem_bytes);
+        if (rc) return rc;
+        k_setup<true><<<nsys, kThreads, plan->setup_smem_bytes, st>>>(D, Q, sQ, G, sG, A, sA, Lfac, Wfac,
+                                                                    Kfac, spd_flag, nullptr, 0);
+    } else {
+        if (!scratch) return QPB200_ERR_BAD_ARG;
+        int rc = set_smem(k_setup<false>, plan->setup_smem_bytes);
+        if (rc) return rc;
+        k_setup<false><<<nsys, kThreads, plan->setup_smem_bytes, st>>>(
+            D, Q, sQ, G, sG, A, sA, Lfac, Wfac, Kfac, spd_flag, scratch, plan->setup_scratch_elems);
+    }
+    CK(cudaGetLastError());
+    return QPB200_OK;
+}
+
+int qpb200_forward(const qpb200_plan* plan, int nbatch, const double* p, int64_t sp, const double* h,
+                   int64_t sh, const double* b, int64_t sb, const double* Lfac, const double* Wfac,
+                   const double* Kfac, int sF, double eps, double stall_tol, double best_tie,
+                   int notImprovedLim, int maxIter, double* zhat, double* lam, double* slacks, double* nus, int* iters,
+                   double* best_resid, double* trace, double* scratch, void* stream) {
+    if (!plan || nbatch <= 0 || !p || !Lfac || !Wfac || !Kfac || !zhat || !lam || !slacks || !iters ||
+        !best_resid)
+        return QPB200_ERR_BAD_ARG;
+    if (plan->nineq > 0 && !h) return QPB200_ERR_BAD_ARG;
+    if (plan->neq > 0 && (!b || !nus)) return QPB200_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    KDims D = dims_of(plan);
+    if (plan->smem_resident) {
+        int rc = set_smem(k_forward<true>, plan->solve_smem_bytes);
+        if (rc) return rc;
+        k_forward<true><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
+            D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, maxIter, zhat, lam,
+            slacks, nus, iters, best_resid, trace, nullptr, 0);
+    } else {
+        if (!scratch) return QPB200_ERR_BAD_ARG;
+        int rc = set_smem(k_forward<false>, plan->solve_smem_bytes);
+        if (rc) return rc;
+        k_forward<false><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
+            D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, maxIter, zhat, lam,
+            slacks, nus, iters, best_resid, trace, scratch, plan->solve_scratch_elems);
+    }
+    CK(cudaGetLastError());
+    return QPB200_OK;
+}
+
+int qpb200_solve_kkt(const qpb200_plan* plan, int nbatch, const double* d, const double* rx,
+                     const double* rs, const double* rz, const double* ry, const double* Lfac,
+                     const double* Wfac, const double* Kfac, int sF, double* dx, double* ds,
+                     double* dz, double* dy, double* scratch, void* stream) {
+    if (!plan || nbatch <= 0 || !d || !rx || !rs || !rz || !Lfac || !Wfac || !Kfac || !dx || !ds || !dz)
+        return QPB200_ERR_BAD_ARG;
+    if (plan->neq > 0 && (!ry || !dy)) return QPB200_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    KDims D = dims_of(plan);
+    BwdOut O;
+    memset(&O, 0, sizeof(O));
+    if (plan->smem_resident) {
+        int rc = set_smem(k_solve_kkt<true, false>, plan->solve_smem_bytes);
+        if (rc) return rc;
+        k_solve_kkt<true, false><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
+            D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz,
+            dy, O, nullptr, 0);
+    } else {
+        if (!scratch) return QPB200_ERR_BAD_ARG;
+        int rc = set_smem(k_solve_kkt<false, false>, plan->solve_smem_bytes);
+        if (rc) return rc;
+        k_solve_kkt<false, false><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
+            D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz,
+            dy, O, scratch, plan->solve_scratch_elems);
+    }
+    CK(cudaGetLastError());
+    return QPB200_OK;
+}
+
+int qpb200_backward(const qpb200_plan* plan, int nbatch, const double* dl_dzhat, const double* zhat,
+                    const double* lam, const double* slacks, const double* nus, const double* Lfac,
+                    const double* Wfac, const double* Kfac, int sF, double* dQ, int mean_Q, double* dp,
+                    int mean_p, double* dG, int mean_G, double* dh, int mean_h, double* dA, int mean_A,
+                    double* db, int mean_b, double* dxv, double* dlamv, double* dnuv, double* scratch,
+                    void* stream) {
+    if (!plan || nbatch <= 0 || !dl_dzhat || !zhat || !lam || !slacks || !Lfac || !Wfac || !Kfac ||
+        !dxv || !dlamv)
+        return QPB200_ERR_BAD_ARG;
+    if (plan->neq > 0 && (!nus || !dnuv)) return QPB200_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    KDims D = dims_of(plan);
+    const int n = plan->nz, m = plan->nineq, e = plan->neq;
+    BwdOut O;
+    O.dQ = dQ; O.dp = dp; O.dG = dG; O.dh = dh; O.dA = dA; O.db = db;
+    O.mQ = mean_Q; O.mp = mean_p; O.mG = mean_G; O.mh = mean_h; O.mA = mean_A; O.mb = mean_b;
+    if (plan->smem_resident) {
+        int rc = set_smem(k_solve_kkt<true, true>, plan->solve_smem_bytes);
+        if (rc) return rc;
+        k_solve_kkt<true, true><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
+            D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac,
+            sF, dxv, nullptr, dlamv, dnuv, O, nullptr, 0);
+    } else {
+        if (!scratch) return QPB200_ERR_BAD_ARG;
+        int rc = set_smem(k_solve_kkt<false, true>, plan->solve_smem_bytes);
+        if (rc) return rc;
+        k_solve_kkt<false, true><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
+            D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac,
+            sF, dxv, nullptr, dlamv, dnuv, O, scratch, plan->solve_scratch_elems);
+    }
+    CK(cudaGetLastError());
+    const int TB = 256;
+    if (dQ && mean_Q)
+        k_mean_outer<<<(n * n + TB - 1) / TB, TB, 0, st>>>(nbatch, n, n, dxv, zhat, zhat, dxv, 0.5, dQ);
+    if (dp && mean_p) k_mean_vec<<<(n + TB - 1) / TB, TB, 0, st>>>(nbatch, n, dxv, 1.0, dp);
+    if (dG && mean_G)
+        k_mean_outer<<<(m * n + TB - 1) / TB, TB, 0, st>>>(nbatch, m, n, dlamv, zhat, lam, dxv, 1.0, dG);
+    if (dh && mean_h) k_mean_vec<<<(m + TB - 1) / TB, TB, 0, st>>>(nbatch, m, dlamv, -1.0, dh);
+    if (e > 0) {
+        if (dA && mean_A)
+            k_mean_outer<<<(e * n + TB - 1) / TB, TB, 0, st>>>(nbatch, e, n, dnuv, zhat, nus, dxv, 1.0, dA);
+        if (db && mean_b) k_mean_vec<<<(e + TB - 1) / TB, TB, 0, st>>>(nbatch, e, dnuv, -1.0, db);
+    }
+    CK(cudaGetLastError());
+    return QPB200_OK;
+}
+
+int qpb200_qp_host(int device, int nbatch, int nz, int nineq, int neq, const double* Q_host,
+                   const double* p_host, const double* G_host, const double* h_host,
+                   const double* A_host, const double* b_host, const double* dl_host, double eps,
+                   int notImprovedLim, int maxIter, double* zhat_host, double* dQ_host,
+                   double* dp_host, double* dG_host, double* dh_host, double* dA_host, double* db_host,
+                   int* spd_flag_host) {
+    qpb200_plan P;
+    int rc = qpb200_plan_init(nz, nineq, neq, &P);
+    if (rc) return rc;
+    if (nbatch <= 0 || !Q_host || !p_host || !zhat_host) return QPB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(device));
+    cudaStream_t st;
+    CK(cudaStreamCreate(&st));
+    const int64_t B = nbatch, n = nz, m = nineq, e = neq;
+    const bool bwd = dl_host != nullptr;
+    // one arena: inputs | factors | outputs | work
+    const int64_t nin = B * (n * n + n + m * n + m + e * n + e + (bwd ? n : 0));
+    const int64_t nfac = B * (P.L_elems + P.W_elems + P.K_elems);
+    const int64_t nout = B * (n + 2 * m + e) + B /*resid*/;
+    const int64_t ngrad = bwd ? B * (n * n + n + m * n + m + e * n + e + n + m + e) : 0;
+    const int64_t nscr = B * (P.solve_scratch_elems > P.setup_scratch_elems ? P.solve_scratch_elems
+                                                                             : P.setup_scratch_elems);
+    double* arena = nullptr;
+    int* iarena = nullptr;
+    CK(cudaMalloc(&arena, (size_t)(nin + nfac + nout + ngrad + nscr + 8) * sizeof(double)));
+    CK(cudaMalloc(&iarena, (size_t)(2 * B) * sizeof(int)));
+    double* q = arena;
+    double* dQm = q; q += B * n * n;
+    double* dpv = q; q += B * n;
+    double* dGm = q; q += B * m * n;
+    double* dhv = q; q += B * m;
+    double* dAm = q; q += B * e * n;
+    double* dbv = q; q += B * e;
+    double* ddl = q; q += bwd ? B * n : 0;
+    double* Lf = q; q += B * P.L_elems;
+    double* Wf = q; q += B * P.W_elems;
+    double* Kf = q; q += B * P.K_elems;
+    double* dz = q; q += B * n;
+    double* dlam = q; q += B * m;
+    double* dsl = q; q += B * m;
+    double* dnu = q; q += B * e;
+    double* dres = q; q += B;
+    double *gQ = nullptr, *gp = nullptr, *gG = nullptr, *gh = nullptr, *gA = nullptr, *gb = nullptr,
+           *wx = nullptr, *wl = nullptr, *wn = nullptr;
+    if (bwd) {
+        gQ = q; q += B * n * n; gp = q; q += B * n; gG = q; q += B * m * n; gh = q; q += B * m;
+        gA = q; q += B * e * n; gb = q; q += B * e; wx = q; q += B * n; wl = q; q += B * m; wn = q; q += B * e;
+    }
+    double* scr = nscr ? q : nullptr;
+    int* dflag = iarena;
+    int* diters = iarena + B;
+#define H2D(dst, src, cnt) if ((cnt) > 0) CK(cudaMemcpyAsync(dst, src, (size_t)(cnt) * sizeof(double), cudaMemcpyHostToDevice, st))
+#define D2H(dst, src, cnt) if ((cnt) > 0 && (dst)) CK(cudaMemcpyAsync(dst, src, (size_t)(cnt) * sizeof(double), cudaMemcpyDeviceToHost, st))
+    H2D(dQm, Q_host, B * n * n); H2D(dpv, p_host, B * n); H2D(dGm, G_host, B * m * n);
+    H2D(dhv, h_host, B * m); H2D(dAm, A_host, B * e * n); H2D(dbv, b_host, B * e);
+    if (bwd) H2D(ddl, dl_host, B * n);
+    rc = qpb200_pre_factor_kkt(&P, nbatch, dQm, n * n, dGm, m * n, dAm, e * n, Lf, Wf, Kf, dflag, scr, st);
+    if (!rc)
+        rc = qpb200_forward(&P, nbatch, dpv, n, dhv, m, dbv, e, Lf, Wf, Kf, 1, eps, 1e-6, 1.5, notImprovedLim, maxIter,
+                            dz, dlam, dsl, e > 0 ? dnu : nullptr, diters, dres, nullptr, scr, st);
+    if (!rc && bwd)
+        rc = qpb200_backward(&P, nbatch, ddl, dz, dlam, dsl, e > 0 ? dnu : nullptr, Lf, Wf, Kf, 1, gQ, 0, gp,
+                             0, gG, 0, gh, 0, e > 0 ? gA : nullptr, 0, e > 0 ? gb : nullptr, 0, wx, wl,
+                             e > 0 ? wn : nullptr, scr, st);
+    if (!rc) {
+        D2H(zhat_host, dz, B * n);
+        if (bwd) {
+            D2H(dQ_host, gQ, B * n * n); D2H(dp_host, gp, B * n); D2H(dG_host, gG, B * m * n);
+            D2H(dh_host, gh, B * m); D2H(dA_host, gA, B * e * n); D2H(db_host, gb, B * e);
+        }
+        if (spd_flag_host)
+            CK(cudaMemcpyAsync(spd_flag_host, dflag, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+        cudaError_t err = cudaStreamSynchronize(st);
+        if (err != cudaSuccess) rc = cuda_fail(err, "cudaStreamSynchronize");
+    }
+#undef H2D
+#undef D2H
+    cudaFree(arena);
+    cudaFree(iarena);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+}  // extern "C"

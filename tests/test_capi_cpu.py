@@ -1,0 +1,71 @@
+"""CPU-only checks of the C-ABI boundary: the library builds, loads, and exports every symbol the
+header declares; plan sizes are sane. No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from qpth_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_all_exported(lib):
+    from qpth_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "qpth_b200.h")).read()
+    declared = set(re.findall(r"\b(qpb200_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+
+
+def test_version_and_error_strings(lib):
+    assert lib.qpb200_version() >= 100
+    assert lib.qpb200_error_string(0) == b"ok"
+    assert b"nineq" in lib.qpb200_error_string(2)
+
+
+def test_plan_shapes(lib):
+    from qpth_b200 import _lib
+    p = _lib.plan_for(100, 100, 0)
+    assert (p.ms, p.neq_pad, p.smem_resident) == (100, 0, 1)
+    assert p.solve_smem_bytes <= 232448 and p.ldw % 8 == 4 and p.lds % 8 == 4
+    p = _lib.plan_for(50, 50, 10)
+    assert (p.neq_pad, p.ms) == (16, 66)
+    p = _lib.plan_for(200, 200, 0)
+    assert p.smem_resident == 0 and p.solve_scratch_elems > 0
+    bad = _lib.Plan()
+    assert lib.qpb200_plan_init(5, 0, 0, ctypes.byref(bad)) == 2      # QPB200_ERR_NO_CONSTRAINTS
+    assert lib.qpb200_plan_init(0, 3, 0, ctypes.byref(bad)) == 1
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from qpth_b200 import QPFunction
+    from qpth_b200._lib import QpthB200Error
+    Q = torch.eye(3, dtype=torch.float64)
+    with pytest.raises(QpthB200Error, match="no CUDA device"):
+        QPFunction()(Q, torch.zeros(3, dtype=torch.float64), torch.eye(3, dtype=torch.float64),
+                     torch.ones(3, dtype=torch.float64), torch.Tensor(), torch.Tensor())
+
+
+def test_util_mirrors_reference_broadcast_rules():
+    import torch
+    from qpth_b200.util import expandParam, extract_nBatch
+    Q = torch.eye(3); p = torch.zeros(5, 3)
+    assert extract_nBatch(Q, p, Q, p[0], torch.Tensor(), torch.Tensor()) == 5
+    X, flag = expandParam(Q, 5, 3)
+    assert flag and X.shape == (5, 3, 3) and X.stride(0) == 0
+    X, flag = expandParam(torch.Tensor(), 5, 3)
+    assert not flag
+    with pytest.raises(RuntimeError, match="Unexpected number of dimensions."):
+        expandParam(torch.zeros(2, 2, 2, 2), 5, 3)

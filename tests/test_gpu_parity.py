@@ -1,0 +1,238 @@
+"""GPU parity: the CUDA path (through QPFunction -> ctypes -> C ABI) against
+ (1) the REAL reference's outputs committed under tests/golden/,
+ (2) the oracle at BASELINE.json's full sizes,
+ (3) solver-independent properties (KKT conditions, .mean(0) rule, linearity of backward).
+Tolerances (fp64): z*, lambda, s, nu <= 1e-8; gradients <= 1e-6 (per-QP relative l2, tests/parity.py).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdipm_oracle as orc
+from oracle.cases import CASES, load_case
+from qpth_b200.problems import random_qp_batch
+from tests.parity import check_against_golden, rel_rows, ZTOL, GTOL
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _run(prob, requires=True, **opts):
+    from qpth_b200 import QPFunction
+    t = {}
+    for k in ("Q", "p", "G", "h", "A", "b"):
+        v = np.asarray(prob[k], dtype=np.float64)
+        if v.size == 0:
+            t[k] = torch.Tensor().to(DEV).double()
+        else:
+            t[k] = torch.tensor(v, dtype=torch.float64, device=DEV, requires_grad=requires)
+    f = QPFunction(verbose=-1, **opts)
+    z = f(t["Q"], t["p"], t["G"], t["h"], t["A"], t["b"])
+    out = dict(zhat=z.detach().cpu().numpy())
+    st = f.last_solve()
+    out["lam"] = st.lam.cpu().numpy()
+    out["slacks"] = st.slacks.cpu().numpy()
+    out["nus"] = None if st.nus is None else st.nus.cpu().numpy()
+    out["iters"] = st.iters.cpu().numpy()
+    out["best_resid"] = st.best_resid.cpu().numpy()
+    if prob.get("dl") is not None and requires:
+        dl = torch.tensor(np.asarray(prob["dl"]).reshape(tuple(z.shape)), dtype=torch.float64, device=DEV)
+        z.backward(dl)
+        out["grads"] = tuple(None if t[k].grad is None else t[k].grad.cpu().numpy()
+                             for k in ("Q", "p", "G", "h", "A", "b"))
+    return out
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_matches_reference_golden(name, golden_dir):
+    prob, gold, full = load_case(name, golden_dir)
+    out = _run(prob)
+    assert out["zhat"].shape == gold["zhat"].shape
+    check_against_golden(out, gold, full, what=name)
+
+
+@pytest.mark.parametrize("cfg", [dict(nBatch=128, nz=100, nineq=100, neq=0),
+                                 dict(nBatch=1024, nz=50, nineq=50, neq=10)])
+def test_full_size_vs_oracle(cfg):
+    """C2 and C3 at BASELINE.json's full sizes against the oracle (per-QP semantics), fresh seed."""
+    pr = random_qp_batch(seed=11, **cfg)
+    if cfg["nBatch"] > 256:     # keep the CPU oracle to a few seconds: check a strided subset
+        idx = np.arange(0, cfg["nBatch"], 8)
+    else:
+        idx = np.arange(cfg["nBatch"])
+    out = _run(pr)
+    sub = {k: (v[idx] if v.shape[0] == cfg["nBatch"] else v) for k, v in pr.items()}
+    ref = orc.qp_solve(sub["Q"], sub["p"], sub["G"], sub["h"], sub["A"], sub["b"], sub["dl"], per_qp=True)
+    assert rel_rows(out["zhat"][idx], ref["zhat"]).max() <= ZTOL
+    for g, r in zip(out["grads"], ref["grads"]):
+        if r is None:
+            assert g is None
+        else:
+            assert rel_rows(g[idx], r, floor=1e-4).max() <= GTOL
+    # never (much) more Newton iterations than the reference's nBatch=1 run; fewer is possible because the
+    # fused-multiply-add arithmetic reaches the eps=1e-12 exit an iteration earlier on some QPs
+    assert (out["iters"][idx] - ref["info"]["iters"]).max() <= 2 and out["iters"].max() <= 20
+
+
+def test_kkt_conditions_full_c2():
+    pr = random_qp_batch(128, 100, 100, 0, seed=5)
+    out = _run(pr, requires=False)
+    z, lam = out["zhat"], out["lam"]
+    stat = np.einsum("bij,bj->bi", pr["Q"], z) + pr["p"] + np.einsum("bmi,bm->bi", pr["G"], lam)
+    assert np.abs(stat).max() < 1e-8
+    assert (np.einsum("bmi,bi->bm", pr["G"], z) - pr["h"]).max() < 1e-9
+    assert lam.min() > -1e-12
+    assert np.abs(lam * (pr["h"] - np.einsum("bmi,bi->bm", pr["G"], z))).max() < 1e-8
+
+
+def test_mean_rule_for_unbatched_inputs():
+    """qp.py:159-177: gradient of an un-batched input == batch MEAN of the batched gradients."""
+    pr = random_qp_batch(6, 12, 8, 3, seed=9)
+    shared = dict(pr)
+    for k in ("Q", "G", "A", "h"):
+        shared[k] = pr[k][0]
+    shared["b"] = pr["b"]            # b must stay consistent with A: rebuild from shared A
+    z0 = np.random.RandomState(1).randn(6, 12)
+    shared["b"] = z0 @ shared["A"].T
+    shared["h"] = shared["h"] + 1.0
+    out_s = _run(shared)
+    full = dict(shared)
+    for k in ("Q", "G", "A", "h"):
+        full[k] = np.broadcast_to(shared[k][None], (6,) + shared[k].shape).copy()
+    out_f = _run(full)
+    assert rel_rows(out_s["zhat"], out_f["zhat"]).max() < 1e-12
+    for k, (gs, gf) in enumerate(zip(out_s["grads"], out_f["grads"])):
+        if k in (0, 2, 3, 4):
+            np.testing.assert_allclose(gs, gf.mean(0), rtol=1e-10, atol=1e-12)
+        else:
+            np.testing.assert_allclose(gs, gf, rtol=1e-10, atol=1e-12)
+
+
+def test_backward_is_linear_in_upstream_gradient():
+    pr = random_qp_batch(16, 30, 20, 4, seed=3)
+    a = _run(pr)
+    pr2 = dict(pr); pr2["dl"] = -2.5 * pr["dl"]
+    b = _run(pr2)
+    for ga, gb in zip(a["grads"], b["grads"]):
+        np.testing.assert_allclose(gb, -2.5 * ga, rtol=1e-9, atol=1e-12)
+
+
+def test_solve_kkt_entry_matches_oracle():
+    """Rows a8/a9: factor_kkt + solve_kkt for arbitrary d and right-hand sides (batch.py:349-372,435-470)."""
+    from qpth_b200 import _lib
+    lib = _lib.load()
+    B, n, m, e = 10, 24, 19, 5
+    pr = random_qp_batch(B, n, m, e, seed=21)
+    rs = np.random.RandomState(22)
+    d = np.exp(rs.uniform(-8, 8, size=(B, m)))
+    rx, rsv, rz, ry = rs.randn(B, n), rs.randn(B, m), rs.randn(B, m), rs.randn(B, e)
+    F = orc.Factors(pr["Q"], pr["G"], pr["A"])
+    F.factor_kkt(d)
+    dx, ds, dz, dy = F.solve_kkt(pr["G"], pr["A"], d, rx, rsv, rz, ry)
+    plan = _lib.plan_for(n, m, e)
+    tt = lambda a: torch.tensor(a, dtype=torch.float64, device=DEV).contiguous()
+    Q, G, A = tt(pr["Q"]), tt(pr["G"]), tt(pr["A"])
+    L = torch.empty(B * plan.L_elems, dtype=torch.float64, device=DEV)
+    W = torch.empty(B * plan.W_elems, dtype=torch.float64, device=DEV)
+    K = torch.empty(B * plan.K_elems, dtype=torch.float64, device=DEV)
+    spd = torch.zeros(B, dtype=torch.int32, device=DEV)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.qpb200_pre_factor_kkt(ctypes.byref(plan), B, P(Q), n * n, P(G), m * n, P(A), e * n,
+                                         P(L), P(W), P(K), P(spd), None, st))
+    td, trx, trs, trz, tr_y = tt(d), tt(rx), tt(rsv), tt(rz), tt(ry)
+    odx = torch.empty(B, n, dtype=torch.float64, device=DEV)
+    ods = torch.empty(B, m, dtype=torch.float64, device=DEV)
+    odz = torch.empty(B, m, dtype=torch.float64, device=DEV)
+    ody = torch.empty(B, e, dtype=torch.float64, device=DEV)
+    _lib.check(lib.qpb200_solve_kkt(ctypes.byref(plan), B, P(td), P(trx), P(trs), P(trz), P(tr_y),
+                                    P(L), P(W), P(K), 1, P(odx), P(ods), P(odz), P(ody), None, st))
+    torch.cuda.synchronize()
+    assert int(spd.sum()) == 0
+    assert rel_rows(odx.cpu().numpy(), dx).max() < 1e-9
+    assert rel_rows(ods.cpu().numpy(), ds).max() < 1e-9
+    assert rel_rows(odz.cpu().numpy(), dz).max() < 1e-9
+    assert rel_rows(ody.cpu().numpy(), dy).max() < 1e-9
+
+
+def test_pre_factor_blocks_match_definition():
+    """pre_factor_kkt (batch.py:375-429): L L^T = Q, W = [A;G] L^-T, K trailing block = Schur complement R."""
+    from qpth_b200 import _lib
+    lib = _lib.load()
+    B, n, m, e = 3, 50, 50, 10
+    pr = random_qp_batch(B, n, m, e, seed=2)
+    plan = _lib.plan_for(n, m, e)
+    tt = lambda a: torch.tensor(a, dtype=torch.float64, device=DEV).contiguous()
+    Q, G, A = tt(pr["Q"]), tt(pr["G"]), tt(pr["A"])
+    L = torch.empty(B, plan.L_elems, dtype=torch.float64, device=DEV)
+    W = torch.empty(B, plan.ms, plan.ldw, dtype=torch.float64, device=DEV)
+    K = torch.empty(B, plan.ms, plan.lds, dtype=torch.float64, device=DEV)
+    spd = torch.zeros(B, dtype=torch.int32, device=DEV)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.qpb200_pre_factor_kkt(ctypes.byref(plan), B, P(Q), n * n, P(G), m * n, P(A), e * n,
+                                         P(L), P(W), P(K), P(spd), None, st))
+    torch.cuda.synchronize()
+    Lp, Wn, Kn = L.cpu().numpy(), W.cpu().numpy()[:, :, :n], K.cpu().numpy()[:, :, :plan.ms]
+    ep = plan.neq_pad
+    tri = np.tril_indices(n)
+    for i in range(B):
+        Ln = np.zeros((n, n)); Ln[tri] = Lp[i][:n * (n + 1) // 2]     # packed lower, row by row
+        assert np.abs(Ln @ Ln.T - pr["Q"][i]).max() < 1e-10 * np.abs(pr["Q"][i]).max()
+        Wref = np.linalg.solve(Ln, np.vstack([pr["A"][i], pr["G"][i]]).T).T
+        assert np.abs(Wn[i][:e] - Wref[:e]).max() < 1e-8 * np.abs(Wref).max()
+        assert np.abs(Wn[i][e:ep]).max() == 0.0
+        assert np.abs(Wn[i][ep:] - Wref[e:]).max() < 1e-8 * np.abs(Wref).max()
+        F = orc.Factors(pr["Q"][i:i + 1], pr["G"][i:i + 1], pr["A"][i:i + 1])
+        Rk = np.tril(Kn[i][ep:, ep:])
+        assert np.abs(Rk - np.tril(F.R[0])).max() < 1e-8 * np.abs(F.R[0]).max()
+
+
+def test_errors_and_shapes():
+    from qpth_b200 import QPFunction
+    dd = dict(dtype=torch.float64, device=DEV)
+    Q = -torch.eye(3, **dd)
+    e = torch.Tensor().to(DEV)
+    with pytest.raises(RuntimeError, match="Q is not SPD."):
+        QPFunction()(Q, torch.zeros(3, **dd), torch.eye(3, **dd), torch.ones(3, **dd), e, e)
+    with pytest.raises(RuntimeError, match="Unexpected number of dimensions."):
+        QPFunction()(torch.eye(3, **dd)[None, None], torch.zeros(3, **dd), torch.eye(3, **dd),
+                     torch.ones(3, **dd), e, e)
+    # all un-batched -> nBatch inferred as 1, output (1, nz)   (qp.py:73-79)
+    z = QPFunction(verbose=-1)(torch.eye(3, **dd), torch.ones(3, **dd), -torch.eye(3, **dd),
+                               torch.zeros(3, **dd), e, e)
+    assert tuple(z.shape) == (1, 3)
+    np.testing.assert_allclose(z.cpu().numpy(), np.zeros((1, 3)), atol=1e-9)   # min 1/2|z|^2 + 1.z, z >= 0
+
+
+def test_fp32_and_cpu_tensors_round_trip():
+    from qpth_b200 import QPFunction
+    pr = random_qp_batch(4, 10, 5, 0, seed=0)
+    t = [torch.tensor(pr[k], dtype=torch.float32) for k in ("Q", "p", "G", "h")]
+    z = QPFunction(verbose=-1)(*t, torch.Tensor(), torch.Tensor())
+    assert z.dtype == torch.float32 and z.device.type == "cpu"
+    ref = orc.qp_solve(pr["Q"], pr["p"], pr["G"], pr["h"], pr["A"], pr["b"])
+    assert rel_rows(z.numpy().astype(np.float64), ref["zhat"]).max() < 1e-4
+
+
+def test_host_buffer_entry_point():
+    """qpb200_qp_host: the whole path on host buffers through the raw C ABI."""
+    from qpth_b200 import _lib
+    lib = _lib.load()
+    B, n, m, e = 8, 20, 15, 5
+    pr = random_qp_batch(B, n, m, e, seed=1)
+    c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    arrs = {k: c(pr[k]) for k in ("Q", "p", "G", "h", "A", "b", "dl")}
+    z = np.empty((B, n)); dQ = np.empty((B, n, n)); dp = np.empty((B, n)); dG = np.empty((B, m, n))
+    dh = np.empty((B, m)); dA = np.empty((B, e, n)); db = np.empty((B, e)); spd = np.zeros(B, dtype=np.int32)
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    _lib.check(lib.qpb200_qp_host(0, B, n, m, e, P(arrs["Q"]), P(arrs["p"]), P(arrs["G"]), P(arrs["h"]),
+                                  P(arrs["A"]), P(arrs["b"]), P(arrs["dl"]), 1e-12, 3, 20,
+                                  P(z), P(dQ), P(dp), P(dG), P(dh), P(dA), P(db), P(spd)))
+    ref = orc.qp_solve(pr["Q"], pr["p"], pr["G"], pr["h"], pr["A"], pr["b"], pr["dl"], per_qp=True)
+    assert rel_rows(z, ref["zhat"]).max() <= ZTOL
+    for g, r in zip((dQ, dp, dG, dh, dA, db), ref["grads"]):
+        assert rel_rows(g, r, floor=1e-4).max() <= GTOL
