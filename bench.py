@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — QPs/sec (fwd+bwd) of the hot path at BASELINE.json's config C2, per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = QPFunction forward + backward over one batch of 128 random dense QPs
+(nz = nineq = 100, neq = 0, fp64; generator of prof-linear.py:64-75).  The path shards
+by QP with no data-path collective, so N GPUs run N independent batches ("weak").
+Rank 0 prints ONE JSON line (contract in the task statement / DESIGN.md section 6).
+
+--impl reference times the CPU baseline instead: oracle/pdipm_torch.py, the batched
+torch-CPU restatement of the reference's algorithm, on all host threads, same workload.
+The real reference (/root/reference) cannot travel to the GPU box.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+from qpth_b200.problems import random_qp_batch, algorithmic_bytes_per_qp, algorithmic_flops_per_qp  # noqa: E402
+
+CFG = dict(nBatch=128, nz=100, nineq=100, neq=0)
+WORKLOAD = "C2: batch=128 nz=100 nineq=100 neq=0 random dense QP, fp64, fwd+bwd (per GPU)"
+METRIC = "QPs/sec (fwd+bwd) batch=128 nz=100 nineq=100"
+NCOPIES = 8          # rotating input sets: 8 x 20.7 MB = 165 MB > 126 MB of L2
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU through NVML (in-process, ~20 us per sample) while the
+    timed region runs. (`nvidia-smi -lms` in a subprocess was measurably perturbing launch latency.)"""
+
+    def __init__(self, index, period=0.02):
+        self.index, self.period, self.rows, self.ok = index, period, [], False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.ok = True
+        except Exception:       # noqa: BLE001 - NVML missing: report that instead of failing the bench
+            self.ok = False
+
+    def start(self):
+        if self.ok:
+            self.th = threading.Thread(target=self._run, daemon=True)
+            self.th.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, rs))
+            except Exception:   # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"]}
+        self._stop.set()
+        self.th.join(timeout=1.0)
+        nv = self.nv
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                "hw_power_brake": 0x80}
+        reasons = set()
+        for _, rs in self.rows:
+            for name, bit in bits.items():
+                if rs & bit:
+                    reasons.add(name)
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(mx), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def make_batches(device, seed0, ncopies, pinned_host=False):
+    out = []
+    for c in range(ncopies):
+        pr = random_qp_batch(seed=seed0 + c, **CFG)
+        if pinned_host:
+            out.append({k: torch.from_numpy(np.ascontiguousarray(pr[k])).pin_memory() for k in ("Q", "p", "G", "h")})
+        else:
+            out.append({k: torch.tensor(pr[k], dtype=torch.float64, device=device, requires_grad=True)
+                        for k in ("Q", "p", "G", "h")})
+    return out
+
+
+def run_b200(args, rank, world, local_rank):
+    from qpth_b200 import QPFunction, _lib
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    B, n, m = CFG["nBatch"], CFG["nz"], CFG["nineq"]
+    f = QPFunction(verbose=-1, check_Q_spd=False)     # fully asynchronous: no host read per step
+    e = torch.Tensor().to(dev).double()
+    dl = torch.ones(B, n, dtype=torch.float64, device=dev)        # dl_dz = 1 (prof-linear.py:117)
+    batches = make_batches(dev, 1000 * rank, NCOPIES)
+
+    def step(i):
+        t = batches[i % NCOPIES]
+        for v in t.values():
+            v.grad = None
+        z = f(t["Q"], t["p"], t["G"], t["h"], e, e)
+        z.backward(dl)
+        return z
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    iters_mean = float(f.last_solve().iters.float().mean())
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        ms = float(tt.item())
+        torch.distributed.barrier()
+
+    # ---- e2e: the same step through QPFunction with HOST (pinned) buffers, H2D + D2H inside the timed region
+    hb = make_batches(dev, 1000 * rank, 2, pinned_host=True)
+    host_out = {k: torch.empty(s, dtype=torch.float64).pin_memory()
+                for k, s in (("z", (B, n)), ("dQ", (B, n, n)), ("dp", (B, n)), ("dG", (B, m, n)), ("dh", (B, m)))}
+    h2d = sum(v.numel() * 8 for v in hb[0].values())
+    d2h = sum(v.numel() * 8 for v in host_out.values())
+
+    def e2e_step(i):
+        src = hb[i % 2]
+        t = {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in src.items()}
+        z = f(t["Q"], t["p"], t["G"], t["h"], e, e)
+        z.backward(dl)
+        host_out["z"].copy_(z.detach(), non_blocking=True)
+        for k, g in (("dQ", "Q"), ("dp", "p"), ("dG", "G"), ("dh", "h")):
+            host_out[k].copy_(t[g].grad, non_blocking=True)
+
+    for i in range(max(3, args.warmup // 2)):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    ksteps = max(5, args.steps // 2)
+    ev0.record()
+    for i in range(ksteps):
+        e2e_step(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    e2e_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    if rank != 0:
+        return None
+
+    # ---- dominant kernel (k_forward) timed alone through the C ABI, on the stream it is launched on
+    plan = _lib.plan_for(n, m, 0)
+    t = batches[0]
+    f64 = dict(dtype=torch.float64, device=dev)
+    L = torch.empty(B * plan.L_elems, **f64); W = torch.empty(B * plan.W_elems, **f64)
+    K = torch.empty(B * plan.K_elems, **f64); spd = torch.zeros(B, dtype=torch.int32, device=dev)
+    zz = torch.empty(B, n, **f64); ll = torch.empty(B, m, **f64); ss = torch.empty(B, m, **f64)
+    iters = torch.empty(B, dtype=torch.int32, device=dev); rr = torch.empty(B, **f64)
+    P = lambda x: ctypes.c_void_p(x.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    Qc, Gc, pc, hc = (t[k].detach().contiguous() for k in ("Q", "G", "p", "h"))
+    _lib.check(lib.qpb200_pre_factor_kkt(ctypes.byref(plan), B, P(Qc), n * n, P(Gc), m * n, None, 0,
+                                         P(L), P(W), P(K), P(spd), None, st))
+    kt = []
+    for i in range(8):
+        ev0.record()
+        _lib.check(lib.qpb200_forward(ctypes.byref(plan), B, P(pc), n, P(hc), m, None, 0, P(L), P(W), P(K), 1,
+                                      1e-12, 1e-6, 1.5, 3, 20, P(zz), P(ll), P(ss), None, P(iters), P(rr),
+                                      None, None, st))
+        ev1.record()
+        torch.cuda.synchronize()
+        kt.append(ev0.elapsed_time(ev1))
+    k_ms = float(np.mean(kt[2:]))
+    # fp64 FMA peak of this box, measured (148 SMs x 4 CTAs x 256 threads x 8 chains)
+    probe_out = torch.empty(148 * 8 * 256, **f64)
+    pk = []
+    for i in range(4):
+        ev0.record()
+        _lib.check(lib.qpb200_dfma_probe(148 * 8, 256, 4096, P(probe_out), st))
+        ev1.record(); torch.cuda.synchronize()
+        pk.append(ev0.elapsed_time(ev1))
+    fp64_peak = 2.0 * 8 * 4096 * 148 * 8 * 256 / (min(pk[1:]) * 1e-3) / 1e12
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    ab = algorithmic_bytes_per_qp(n, m, 0)
+    fwd_bytes = (ab["fwd_in"] + ab["fwd_out"]) * B
+    achieved = fwd_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json"))).get("k_forward_dram_bytes")
+    except (OSError, ValueError):
+        pass
+    it_mean = float(iters.float().mean())
+    flops = algorithmic_flops_per_qp(n, m, 0, it_mean) * B
+    total_qps = world * B * args.steps
+    line = {
+        "metric": METRIC, "value": total_qps / (ms * 1e-3), "unit": "QPs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (seeded prof-linear.py generator)", "impl": "b200",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "options": "eps=1e-12 maxIter=20 notImprovedLim=3 verbose=-1 check_Q_spd=False",
+                   "l2": "inputs rotate over %d independent batches (%.0f MB > 126 MB L2)" % (NCOPIES, NCOPIES * h2d / 1e6),
+                   "mean_newton_iters": iters_mean},
+        "e2e": {"value": world * B * ksteps / (e2e_ms * 1e-3), "unit": "QPs/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": ksteps,
+                "api": "qpth_b200.QPFunction on pinned host tensors: H2D, fwd, bwd, D2H of z* and all gradients"},
+        "gpu_launches": 3 * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_forward", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": fwd_bytes,
+                     "note": "latency/fp64-bound path (SURVEY 8d): HBM fraction is small by construction",
+                     "fp64": {"achieved_tflops": flops / (k_ms * 1e-3) / 1e12, "peak_tflops_measured": fp64_peak,
+                              "frac": flops / (k_ms * 1e-3) / 1e12 / fp64_peak}},
+        "cpu_baseline": cpu_baseline(sample_reps=3),
+    }
+    return line
+
+
+def best_cpu_threads(pt, T, dl):
+    """Batched 100x100 LAPACK calls do not scale to every core of a big host: use the thread count that
+    maximises the port's own throughput (one calibration pass each) so the CPU baseline is not handicapped."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (1, 4, 8, 16, 32, 64, ncpu // 2, ncpu) if 1 <= c <= ncpu})
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        pt.qp_fwd_bwd(T["Q"], T["p"], T["G"], T["h"], T["A"], T["b"], dl)
+        t0 = time.perf_counter()
+        pt.qp_fwd_bwd(T["Q"], T["p"], T["G"], T["h"], T["A"], T["b"], dl)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    return best
+
+
+def cpu_baseline(sample_reps=3, threads=None):
+    """The CPU port (oracle/pdipm_torch.py) on the host cores: fwd+bwd over the C2 batch."""
+    from oracle import pdipm_torch as pt
+    pr = random_qp_batch(seed=0, **CFG)
+    T = {k: torch.from_numpy(np.ascontiguousarray(pr[k])) for k in ("Q", "p", "G", "h", "A", "b")}
+    dl = torch.ones(CFG["nBatch"], CFG["nz"], dtype=torch.float64)
+    torch.set_num_threads(threads or best_cpu_threads(pt, T, dl))
+    pt.qp_fwd_bwd(T["Q"], T["p"], T["G"], T["h"], T["A"], T["b"], dl)      # warm-up
+    ts = []
+    for _ in range(sample_reps):
+        t0 = time.perf_counter()
+        pt.qp_fwd_bwd(T["Q"], T["p"], T["G"], T["h"], T["A"], T["b"], dl)
+        ts.append(time.perf_counter() - t0)
+    return {"value": CFG["nBatch"] / min(ts), "unit": "QPs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d x the full C2 batch (128 QPs, fwd+bwd), best of %d, oracle/pdipm_torch.py, thread count calibrated" % (sample_reps, sample_reps),
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port on all host threads, same workload, metric and unit."""
+    if rank != 0:
+        return None
+    from oracle import pdipm_torch as pt
+    batches = []
+    for c in range(2):
+        pr = random_qp_batch(seed=c, **CFG)
+        batches.append({k: torch.from_numpy(np.ascontiguousarray(pr[k])) for k in ("Q", "p", "G", "h", "A", "b")})
+    dl = torch.ones(CFG["nBatch"], CFG["nz"], dtype=torch.float64)
+    torch.set_num_threads(best_cpu_threads(pt, batches[0], dl))
+
+    def step(i):
+        T = batches[i % 2]
+        pt.qp_fwd_bwd(T["Q"], T["p"], T["G"], T["h"], T["A"], T["b"], dl)
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    val = CFG["nBatch"] * args.steps / dt
+    cb = {"value": val, "unit": "QPs/s", "cores": torch.get_num_threads(), "kind": "port",
+          "sample": "each step = the full C2 batch (128 QPs, fwd+bwd) on the host CPU; thread count calibrated for best throughput", "host_cpus": os.cpu_count()}
+    return {"metric": METRIC, "value": val, "unit": "QPs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (seeded prof-linear.py generator)",
+            "impl": "reference",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": CFG["nBatch"],
+                       "note": "CPU arm: oracle/pdipm_torch.py (batched torch-CPU restatement of qpth's PDIPM); rank 0 only"},
+            "cpu_baseline": cb,
+            "e2e": {"value": val, "unit": "QPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = run_b200(args, rank, world, local_rank)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

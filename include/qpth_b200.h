@@ -118,6 +118,11 @@ int qpb200_solve_kkt(const qpb200_plan* plan, int nbatch,
                      double* dx, double* ds, double* dz, double* dy,
                      double* scratch, void* stream);
 
+/* Measurement aid: launches blocks x threads threads each issuing 8*iters dependent-chain-free fp64 FMAs
+ * (2*8*iters*blocks*threads flops); out needs blocks*threads doubles. bench.py times it with CUDA
+ * events to obtain the fp64 roofline denominator on the box it runs on. */
+int qpb200_dfma_probe(int blocks, int threads, int iters, double* out, void* stream);
+
 /* Whole path on HOST buffers (pageable or pinned): H2D, pre_factor_kkt, forward,
  * backward, D2H, on `device`; synchronises before returning.  All six inputs
  * batched (nbatch leading dimension); gradients may be NULL to skip backward. */

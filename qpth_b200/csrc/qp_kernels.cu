@@ -631,6 +631,18 @@ __global__ void k_mean_vec(int B, int len, const double* __restrict__ u, double 
     out[idx] = s * scale / (double)B;
 }
 
+// fp64 FMA issue-rate probe: 8 independent DFMA chains per thread (roofline denominator for bench.py)
+__global__ void k_dfma_probe(int iters, double* out) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+           a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
@@ -847,6 +859,13 @@ int qpb200_backward(const qpb200_plan* plan, int nbatch, const double* dl_dzhat,
             k_mean_outer<<<(e * n + TB - 1) / TB, TB, 0, st>>>(nbatch, e, n, dnuv, zhat, nus, dxv, 1.0, dA);
         if (db && mean_b) k_mean_vec<<<(e + TB - 1) / TB, TB, 0, st>>>(nbatch, e, dnuv, -1.0, db);
     }
+    CK(cudaGetLastError());
+    return QPB200_OK;
+}
+
+int qpb200_dfma_probe(int blocks, int threads, int iters, double* out, void* stream) {
+    if (blocks <= 0 || threads <= 0 || iters <= 0 || !out) return QPB200_ERR_BAD_ARG;
+    k_dfma_probe<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, out);
     CK(cudaGetLastError());
     return QPB200_OK;
 }
