@@ -44,12 +44,14 @@ typedef struct qpb200_plan {
     int nz, nineq, neq;
     int neq_pad;            /* neq rounded up to a multiple of 8 (identity-padded rows) */
     int ms;                 /* neq_pad + nineq: order of the reduced KKT system S */
+    int ms_pad;             /* ms rounded up to a multiple of 8 (identity rows): rows of the stored K */
     int ldw, lds, rows_s, vl;   /* shared-memory leading dimensions / row counts */
     int smem_resident;      /* 1: W and the S workspace live in shared memory; 0: global scratch */
     int threads;            /* CTA size the kernels are launched with */
-    int64_t L_elems;        /* per system: chol(Q), nz*nz doubles (lower, row-major)      [replaces Q_LU]  */
-    int64_t W_elems;        /* per system: [A;G] L^-T, ms*nz doubles                      [whitened G, A]  */
-    int64_t K_elems;        /* per system: block-Cholesky template of S, ms*ms doubles    [replaces S_LU,R] */
+    int fast;               /* 1: compact shared-memory kernels (register-resident Cholesky, nineq <= 104) */
+    int64_t L_elems;        /* per system: chol(Q), packed lower triangle, row by row    [replaces Q_LU]  */
+    int64_t W_elems;        /* per system: [A;G] L^-T, ms rows with stride ldw           [whitened G, A]  */
+    int64_t K_elems;        /* per system: block-Cholesky template of S, ms_pad x lds    [replaces S_LU,R] */
     int64_t setup_scratch_elems;   /* per system, only when smem_resident == 0 (else 0) */
     int64_t solve_scratch_elems;   /* per QP,     only when smem_resident == 0 (else 0) */
     int64_t setup_smem_bytes, solve_smem_bytes;

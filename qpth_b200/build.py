@@ -6,8 +6,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "qp_kernels.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", "qp_device.cuh"),
-              os.path.join(os.path.dirname(HERE), "include", "qpth_b200.h")]
+import glob  # noqa: E402
+
+DEPS = sorted(glob.glob(os.path.join(HERE, "csrc", "*"))) + [os.path.join(os.path.dirname(HERE), "include", "qpth_b200.h")]
 OUT = os.path.join(HERE, "libqpth_b200.so")
 
 

@@ -20,6 +20,7 @@
 
 #include "../../include/qpth_b200.h"
 #include "qp_device.cuh"
+#include "qp_fast.cuh"
 
 using namespace qpb;
 
@@ -29,10 +30,11 @@ constexpr int kThreads = 256;
 constexpr int kMaxSmem = 232448 - 1024;   // 227 KB opt-in limit per CTA on sm_100, minus static smem slack
 
 struct KDims {
-    int n, m, e, ep, ms;
+    int n, m, e, ep, ms, msp;   // msp = ms rounded up to a multiple of 8 (identity padded)
     int ldw, lds, rows_s, vl;
     int lp;          // doubles in the packed lower factor L (rounded up to even)
 };
+constexpr int kTabDoubles = 24;   // 96 uint16 tile-table entries for chol_v2
 
 __host__ __device__ inline int ld_for(int c) {
     int v = c < 4 ? 4 : c;
@@ -48,7 +50,7 @@ enum Vec {
 constexpr int kRedDoubles = 4 * 32;
 
 // vector slots + reduction scratch + 2 mbarriers (16 B)
-__host__ __device__ inline size_t solve_vec_doubles(int vl) { return (size_t)V_COUNT * vl + kRedDoubles + 2; }
+__host__ __device__ inline size_t solve_vec_doubles(int vl) { return (size_t)V_COUNT * vl + kRedDoubles + 2 + 24; }
 
 // Global-scratch fallback of the K -> S copy (shared-memory mode uses one TMA bulk copy instead).
 __device__ __forceinline__ void copy_K(double* LS, const double* Kg, int total, int tid, int nt) {
@@ -121,7 +123,7 @@ k_setup(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __restr
 
     double* Lg = Lfac + (int64_t)sys * D.lp;                 // packed lower
     double* Wg = Wfac + (int64_t)sys * ms * D.ldw;           // row stride ldw (= the SMEM layout)
-    double* Kg = Kfac + (int64_t)sys * ms * D.lds;           // row stride lds (= the SMEM layout)
+    double* Kg = Kfac + (int64_t)sys * D.msp * D.lds;        // msp rows, row stride lds (= the SMEM layout)
     for (int i = tid; i < n * n; i += nt) {
         const int r = i / n, c = i - r * n;
         if (c <= r) Lg[(r * (r + 1)) / 2 + c] = RA[r * ldn + c];
@@ -162,9 +164,17 @@ k_setup(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __restr
     }
     __syncthreads();
     if (ep > 0) chol_partial(RA, ldk, ms, 0, ep, nullptr, 0, 0, dinv, nullptr, tid, nt);
-    for (int i = tid; i < ms * D.lds; i += nt) {
+    for (int i = tid; i < ms * ldk; i += nt) {                  // clean upper triangle (DMMA tiles spill into it)
+        const int r = i / ldk, c = i - r * ldk;
+        if (c > r) RA[i] = 0.0;
+    }
+    __syncthreads();
+    // inverted diagonal blocks of the pre-factored equality columns ride along in the upper triangle
+    for (int blk = tid >> 5; blk < ep / 8; blk += nt >> 5) invert_diag8(RA, ldk, 8 * blk, 8, tid & 31);
+    __syncthreads();
+    for (int i = tid; i < D.msp * D.lds; i += nt) {             // msp rows: identity-padded to a multiple of 8
         const int r = i / D.lds, c = i - r * D.lds;
-        Kg[i] = (c <= r && c < ms) ? RA[r * ldk + c] : 0.0;
+        Kg[i] = (r < ms) ? ((c < ms) ? RA[r * ldk + c] : 0.0) : (r == c ? 1.0 : 0.0);
     }
 }
 
@@ -178,6 +188,7 @@ struct Ctx {
     double* vec;        // vector slots
     double* red;        // reduction scratch
     uint64_t* bar;      // [0]: W + L staged, [1]: K -> LS copies       (shared-memory mode only)
+    uint16_t* tab;      // chol_v2 tile table
     const double* Kg;   // K template in global memory (row stride lds)
     uint32_t kphase;    // parity of the next K copy completion
     bool kpending;
@@ -217,7 +228,7 @@ __device__ __forceinline__ Ctx make_ctx(const KDims& D, double* smem, double* gs
     const int64_t sys = sF ? qp : 0;
     const double* Lg = Lfac + sys * (int64_t)D.lp;
     const double* Wg = Wfac + sys * (int64_t)D.ms * D.ldw;
-    c.Kg = Kfac + sys * (int64_t)D.ms * D.lds;
+    c.Kg = Kfac + sys * (int64_t)D.msp * D.lds;
     c.kphase = 0;
     c.kpending = false;
     const int tid = threadIdx.x;
@@ -228,12 +239,14 @@ __device__ __forceinline__ Ctx make_ctx(const KDims& D, double* smem, double* gs
         c.vec = Lp + D.lp;
         c.red = c.vec + (size_t)V_COUNT * D.vl;
         c.bar = reinterpret_cast<uint64_t*>(c.red + kRedDoubles);
+        c.tab = reinterpret_cast<uint16_t*>(c.red + kRedDoubles + 2);
         c.W = W;
         c.Lp = Lp;
         if (tid == 0) {
             mbar_init(c.bar, 1);
             mbar_init(c.bar + 1, 1);
         }
+        build_tile_table(c.tab, (D.ms - D.ep + 7) >> 3, tid);
         __syncthreads();
         if (tid < 32) {
             const uint32_t wb = (uint32_t)(D.ms * D.ldw * 8), lb = (uint32_t)(D.lp * 8);
@@ -251,6 +264,7 @@ __device__ __forceinline__ Ctx make_ctx(const KDims& D, double* smem, double* gs
         c.vec = smem;
         c.red = c.vec + (size_t)V_COUNT * D.vl;
         c.bar = nullptr;
+        c.tab = nullptr;
         c.kpending = true;
     }
     return c;
@@ -260,7 +274,7 @@ __device__ __forceinline__ Ctx make_ctx(const KDims& D, double* smem, double* gs
 
 // factor_kkt + the forward half of solve_kkt: on entry V_AUG holds -h_full (length ms) and V_D holds d.
 // On exit V_W holds w = -S^-1 h_full. Destroys V_AUG, V_T0.
-template <bool kSmem>
+template <bool kSmem, bool kV2>
 __device__ __forceinline__ void factor_and_solve(const KDims& D, Ctx& C, int tid, int nt) {
     double* aug = VEC(V_AUG);
     wait_K<kSmem>(D, C, tid, nt);
@@ -269,20 +283,32 @@ __device__ __forceinline__ void factor_and_solve(const KDims& D, Ctx& C, int tid
     const FullIdx at{D.lds};
     if (D.ep > 0) {
         // equality block: forward-substitute the first ep entries with the pre-factored L11 / L21
-        trsv_fwd(C.LS, at, D.ms, 0, D.ep, VEC(V_DINV), aug, VEC(V_T0), tid, nt);
+        if (kV2) trsv_fwd_T(C.LS, D.lds, D.ms, 0, D.ep, VEC(V_DINV), aug, VEC(V_T0), tid, nt);
+        else trsv_fwd(C.LS, at, D.ms, 0, D.ep, VEC(V_DINV), aug, VEC(V_T0), tid, nt);
         for (int i = tid; i < D.ep; i += nt) aug[i] = VEC(V_T0)[i];
         __syncthreads();
     }
-    chol_partial(C.LS, D.lds, D.ms, D.ep, D.ms, aug, 0, 1, VEC(V_DINV), nullptr, tid, nt);
-    trsv_bwd(C.LS, at, D.ms, VEC(V_DINV), aug, VEC(V_W), tid, nt);
+    if (kV2) {
+        chol_v2(C.LS, D.lds, D.ms, D.ep, aug, VEC(V_DINV), C.tab, tid);
+        trsv_bwd_T(C.LS, D.lds, D.ms, VEC(V_DINV), aug, VEC(V_W), tid, nt);
+    } else {
+        chol_partial(C.LS, D.lds, D.ms, D.ep, D.ms, aug, 0, 1, VEC(V_DINV), nullptr, tid, nt);
+        trsv_bwd(C.LS, at, D.ms, VEC(V_DINV), aug, VEC(V_W), tid, nt);
+    }
 }
 
 // Solve with the factor already in LS: rhs in V_T1 (destroyed) -> result in `out`.
+template <bool kV2>
 __device__ __forceinline__ void solve_with_factor(const KDims& D, const Ctx& C, double* out, int tid,
                                                   int nt) {
-    const FullIdx at{D.lds};
-    trsv_fwd(C.LS, at, D.ms, 0, D.ms, VEC(V_DINV), VEC(V_T1), VEC(V_T0), tid, nt);
-    trsv_bwd(C.LS, at, D.ms, VEC(V_DINV), VEC(V_T0), out, tid, nt);
+    if (kV2) {
+        trsv_fwd_T(C.LS, D.lds, D.ms, 0, D.ms, VEC(V_DINV), VEC(V_T1), VEC(V_T0), tid, nt);
+        trsv_bwd_T(C.LS, D.lds, D.ms, VEC(V_DINV), VEC(V_T0), out, tid, nt);
+    } else {
+        const FullIdx at{D.lds};
+        trsv_fwd(C.LS, at, D.ms, 0, D.ms, VEC(V_DINV), VEC(V_T1), VEC(V_T0), tid, nt);
+        trsv_bwd(C.LS, at, D.ms, VEC(V_DINV), VEC(V_T0), out, tid, nt);
+    }
 }
 
 // x~ = L^-1 x: V_T1 (destroyed) -> dst.  x = L^-T x~: u (destroyed) -> out.
@@ -302,7 +328,7 @@ __device__ __forceinline__ void load_dinvs(const KDims& D, const Ctx& C, int tid
 // ---------------------------------------------------------------------------------------------
 // k_forward: the PDIPM loop (batch.py:47-207), per-QP semantics.
 // ---------------------------------------------------------------------------------------------
-template <bool kSmem>
+template <bool kSmem, bool kV2>
 __global__ void __launch_bounds__(kThreads, 1)
 k_forward(KDims D, const double* __restrict__ p, int64_t sp, const double* __restrict__ h,
           int64_t sh, const double* __restrict__ b, int64_t sb, const double* __restrict__ Lfac,
@@ -345,7 +371,7 @@ k_forward(KDims D, const double* __restrict__ p, int64_t sp, const double* __res
     __syncthreads();
     for (int i = tid; i < ms; i += nt) aug[i] = -(hW[i] + hb[i]);
     __syncthreads();
-    factor_and_solve<kSmem>(D, C, tid, nt);
+    factor_and_solve<kSmem, kV2>(D, C, tid, nt);
     issue_K<kSmem>(D, C, tid);
     finish_dxt(C.W, D.ldw, ms, n, w, pt, xt, part, D.vl, tid, nt);   // x~ = -p~ - W^T w
     {
@@ -425,7 +451,7 @@ k_forward(KDims D, const double* __restrict__ p, int64_t sp, const double* __res
             aug[i] = -hfull;
         }
         __syncthreads();
-        factor_and_solve<kSmem>(D, C, tid, nt);                 // w = [dy_aff; dz_aff]
+        factor_and_solve<kSmem, kV2>(D, C, tid, nt);                 // w = [dy_aff; dz_aff]
         // ---- affine step length and sigma (batch.py:160-168)
         double mn[2] = {INFINITY, INFINITY};
         for (int i = ep + tid; i < ms; i += nt) {
@@ -460,7 +486,7 @@ k_forward(KDims D, const double* __restrict__ p, int64_t sp, const double* __res
             }
             __syncthreads();
         }
-        solve_with_factor(D, C, wc, tid, nt);                   // wc = [dy_cor; dz_cor]
+        solve_with_factor<kV2>(D, C, wc, tid, nt);                   // wc = [dy_cor; dz_cor]
         issue_K<kSmem>(D, C, tid);                              // next factor_kkt's copy of K overlaps the rest
         // ---- combined direction, step length, update (batch.py:185-203)
         mn[0] = INFINITY; mn[1] = INFINITY;
@@ -518,7 +544,7 @@ struct BwdOut {
     int mQ, mp, mG, mh, mA, mb;      // 1 = mean-reduced elsewhere (skip per-QP write)
 };
 
-template <bool kSmem, bool kBackward>
+template <bool kSmem, bool kV2, bool kBackward>
 __global__ void __launch_bounds__(kThreads, 1)
 k_solve_kkt(KDims D, const double* __restrict__ d_in, const double* __restrict__ rx_in,
             const double* __restrict__ rs_in, const double* __restrict__ rz_in,
@@ -564,7 +590,7 @@ k_solve_kkt(KDims D, const double* __restrict__ d_in, const double* __restrict__
     __syncthreads();
     for (int i = tid; i < ms; i += nt) aug[i] = -(VEC(V_C2)[i] + hW[i]);
     __syncthreads();
-    factor_and_solve<kSmem>(D, C, tid, nt);                     // w = [dy; dz]
+    factor_and_solve<kSmem, kV2>(D, C, tid, nt);                     // w = [dy; dz]
     finish_dxt(C.W, D.ldw, ms, n, w, t, dxt, part, D.vl, tid, nt);
     unwhiten(D, C, dxt, VEC(V_XT), tid, nt);                    // dx = L^-T dx~
     const double* dx = VEC(V_XT);
@@ -631,6 +657,442 @@ __global__ void k_mean_vec(int B, int len, const double* __restrict__ u, double 
     out[idx] = s * scale / (double)B;
 }
 
+
+// =============================================================================================
+// FAST PATH (shared-memory resident, padded to 8, compact code): k_forward_fast / k_kkt_fast
+// =============================================================================================
+namespace fk {
+using namespace qpb::fast;
+enum FVec { F_PT = 0, F_XT, F_RXT, F_S, F_V, F_RV, F_HW, F_W, F_DSA, F_DS, F_D, F_BXT, F_BS, F_BV, F_HB,
+            F_DINV, F_DINVL, F_AUG, F_T0, F_T1, F_COUNT };
+
+struct FLayout {              // offsets in doubles into the dynamic shared array
+    int W, LS, Lp, vec, red, bar, tab;
+    int vl;
+};
+__host__ __device__ inline int fast_vl(int n, int msp) { return ((n > msp ? n : msp) + 7) & ~7; }
+__host__ __device__ inline FLayout fast_layout(const KDims& D) {
+    FLayout L;
+    L.vl = fast_vl(D.n, D.msp);
+    L.W = 0;
+    L.LS = L.W + D.ms * D.ldw;
+    L.Lp = L.LS + D.msp * D.lds;
+    L.vec = L.Lp + D.lp;
+    L.red = L.vec + F_COUNT * L.vl;
+    L.bar = L.red + kRedDoubles;
+    L.tab = L.bar + 2;
+    return L;
+}
+__host__ __device__ inline size_t fast_smem_doubles(const KDims& D) {
+    const FLayout L = fast_layout(D);
+    return (size_t)L.tab + kTabDoubles;
+}
+
+struct FCtx {
+    FLayout L;
+    const double* Kg;
+    uint32_t kphase;
+    bool kpending;
+};
+#define FV(i) (C.L.vec + (i) * C.L.vl)
+
+__device__ __forceinline__ void f_issue_K(const KDims& D, FCtx& C) {
+    QPB_SMEM;
+    const int tid = threadIdx.x;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(qsm + C.L.bar);
+    if (tid < 32) {
+        fence_proxy_async();
+        const uint32_t bytes = (uint32_t)(D.msp * D.lds * 8);
+        if (tid == 0) mbar_expect_tx(bar + 1, bytes);
+        __syncwarp();
+        bulk_issue_warp(qsm + C.L.LS, C.Kg, bytes, bar + 1, tid);
+    }
+    C.kpending = true;
+}
+__device__ __forceinline__ void f_wait_K(FCtx& C) {
+    QPB_SMEM;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(qsm + C.L.bar);
+    mbar_wait(bar + 1, C.kphase);
+    C.kphase ^= 1u;
+    C.kpending = false;
+}
+
+// Stage W and packed L with TMA, start the first K copy, build the tile table.
+__device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double* Lfac, const double* Wfac,
+                                           const double* Kfac, int sF) {
+    QPB_SMEM;
+    FCtx C;
+    C.L = fast_layout(D);
+    const int64_t sys = sF ? qp : 0;
+    const double* Lg = Lfac + sys * (int64_t)D.lp;
+    const double* Wg = Wfac + sys * (int64_t)D.ms * D.ldw;
+    C.Kg = Kfac + sys * (int64_t)D.msp * D.lds;
+    C.kphase = 0;
+    C.kpending = false;
+    const int tid = threadIdx.x;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(qsm + C.L.bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+    }
+    build_tile_table(reinterpret_cast<uint16_t*>(qsm + C.L.tab), (D.msp - D.ep) >> 3, tid);
+    __syncthreads();
+    if (tid < 32) {
+        const uint32_t wb = (uint32_t)(D.ms * D.ldw * 8), lb = (uint32_t)(D.lp * 8);
+        if (tid == 0) mbar_expect_tx(bar, wb + lb);
+        __syncwarp();
+        bulk_issue_warp(qsm + C.L.W, Wg, wb, bar, tid);
+        bulk_issue_warp(qsm + C.L.Lp, Lg, lb, bar, tid);
+    }
+    f_issue_K(D, C);
+    mbar_wait(bar, 0);
+    // reciprocal diagonals of L (packed) and of the pre-factored equality block
+    _Pragma("unroll 1") for (int i = tid; i < D.n; i += kNT) qsm[FV(F_DINVL) + i] = 1.0 / qsm[C.L.Lp + (i * (i + 1)) / 2 + i];
+    _Pragma("unroll 1") for (int i = tid; i < D.ep; i += kNT) qsm[FV(F_DINV) + i] = 1.0 / C.Kg[(int64_t)i * D.lds + i];
+    return C;
+}
+
+// factor_kkt + first half of solve_kkt: F_AUG = -h_full (pad entries 0), F_D = d  ->  F_W = -S^-1 h_full
+__device__ __forceinline__ void f_factor_and_solve(const KDims& D, FCtx& C) {
+    QPB_SMEM;
+    const int tid = threadIdx.x;
+    f_wait_K(C);
+    _Pragma("unroll 1") for (int i = D.ep + tid; i < D.ms; i += kNT) qsm[C.L.LS + i * D.lds + i] += 1.0 / qsm[FV(F_D) + i];
+    __syncthreads();
+    if (D.ep > 0) {
+        f_trsv_fwd(C.L.LS, D.lds, D.msp, 0, D.ep, FV(F_DINV), FV(F_AUG), FV(F_T0));
+        _Pragma("unroll 1") for (int i = tid; i < D.ep; i += kNT) qsm[FV(F_AUG) + i] = qsm[FV(F_T0) + i];
+        __syncthreads();
+    }
+    f_chol(C.L.LS, D.lds, D.msp, D.ep, FV(F_AUG), FV(F_DINV), C.L.tab);
+    QPB_TICK(32);   // (chol internals are 20..27)
+    f_trsv_bwd(C.L.LS, D.lds, D.msp, FV(F_DINV), FV(F_AUG), FV(F_W));
+    QPB_TICK(33);   // backward substitution
+}
+
+__device__ __forceinline__ double f_step_fix(double v) { return (isinf(v) && v > 0.0) ? 1.0 : v; }
+}  // namespace fk
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* __restrict__ h, int64_t sh,
+               const double* __restrict__ b, int64_t sb, const double* __restrict__ Lfac,
+               const double* __restrict__ Wfac, const double* __restrict__ Kfac, int sF, double eps,
+               double stall_tol, double best_tie, int notImprovedLim, int maxIter,
+               double* __restrict__ zhat, double* __restrict__ lam, double* __restrict__ slacks,
+               double* __restrict__ nus, int* __restrict__ iters_out, double* __restrict__ resid_out,
+               double* __restrict__ trace) {
+    using namespace fk;
+    QPB_SMEM;
+    const int tid = threadIdx.x;
+    const int qp = blockIdx.x;
+    const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
+#ifdef QPB_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_tlast = clock64();
+#endif
+    FCtx C = f_make_ctx(D, qp, Lfac, Wfac, Kfac, sF);
+    QPB_TICK(0);
+    const int W = C.L.W, ldw = D.ldw;
+    const int pt = FV(F_PT), xt = FV(F_XT), rxt = FV(F_RXT), s = FV(F_S), v = FV(F_V), rv = FV(F_RV),
+              hW = FV(F_HW), w = FV(F_W), dsa = FV(F_DSA), ds = FV(F_DS), d = FV(F_D), hb = FV(F_HB),
+              aug = FV(F_AUG), t0 = FV(F_T0), t1 = FV(F_T1);
+
+    const double* pg = p + (int64_t)qp * sp;
+    const double* hg = h + (int64_t)qp * sh;
+    const double* bg = (e > 0) ? (b + (int64_t)qp * sb) : nullptr;
+    _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[t1 + i] = pg[i];
+    _Pragma("unroll 1") for (int i = tid; i < msp; i += kNT) {
+        double val = 0.0;
+        if (i < e) val = bg[i];
+        else if (i >= ep && i < ms) val = hg[i - ep];
+        qsm[hb + i] = val;
+        qsm[d + i] = 1.0;
+        qsm[s + i] = 0.0;
+        qsm[v + i] = 0.0;
+        qsm[aug + i] = 0.0;
+        qsm[w + i] = 0.0;
+    }
+    __syncthreads();
+    QPB_TICK(1);
+    f_whiten(C.L.Lp, n, FV(F_DINVL), t1, pt);                   // p~ = L^-1 p
+    QPB_TICK(2);
+
+    // ---- initial point: solve_kkt(p, 0, -h, -b) with d = 1   (batch.py:61-67)
+    f_matvec_rows1(W, ldw, ms, n, pt, hW);
+    __syncthreads();
+    _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) qsm[aug + i] = -(qsm[hW + i] + qsm[hb + i]);
+    __syncthreads();
+    f_factor_and_solve(D, C);
+    f_issue_K(D, C);
+    f_matvec_cols(W, ldw, ms, n, w, t0, t1, xt, pt, -1.0, -1, -1.0);   // x~ = -p~ - W^T w
+    {
+        double mn[2] = {INFINITY, INFINITY};
+        _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) {
+            const double wi = qsm[w + i];
+            qsm[v + i] = wi;
+            if (i >= ep) {
+                qsm[s + i] = -wi;
+                mn[0] = fmin(mn[0], -wi);
+                mn[1] = fmin(mn[1], wi);
+            }
+        }
+        f_reduce_min2(mn, C.L.red);
+        _Pragma("unroll 1") for (int i = ep + tid; i < ms; i += kNT) {               // slacks and duals >= 1 (batch.py:77-87)
+            if (mn[0] < 0.0) qsm[s + i] -= mn[0] - 1.0;
+            if (mn[1] < 0.0) qsm[v + i] -= mn[1] - 1.0;
+        }
+        __syncthreads();
+    }
+
+    double best = 0.0, ret_resid = 0.0;
+    int nNot = 0, iters_run = 0;
+    const double dm = (double)m;
+    for (int it = 0; it < maxIter; ++it) {
+        iters_run = it + 1;
+        // ---- residuals (batch.py:94-107)
+        QPB_TICK(3);
+        f_matvec_cols(W, ldw, ms, n, v, t0, t1, rxt, xt, 1.0, pt, 1.0);      // r~x = x~ + p~ + W^T [y;z]
+        QPB_TICK(4);
+        f_matvec_rows2(W, ldw, ms, n, xt, rxt, rv, hW);                      // W x~ , W r~x
+        __syncthreads();
+        QPB_TICK(5);
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};                   // |ry|^2, |rz|^2, |L r~x|^2, s.z
+        _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) {
+            const double r = qsm[rv + i] - qsm[hb + i] + ((i >= ep) ? qsm[s + i] : 0.0);
+            qsm[rv + i] = r;
+            if (i < ep) acc[0] = fma(r, r, acc[0]);
+            else { acc[1] = fma(r, r, acc[1]); acc[3] = fma(qsm[s + i], qsm[v + i], acc[3]); }
+        }
+        QPB_TICK(6);
+        acc[2] = f_tri_norm2(C.L.Lp, n, rxt);
+        QPB_TICK(7);
+        f_reduce_sum4(acc, C.L.red);
+        QPB_TICK(8);
+        const double mu = fabs(acc[3] / dm);
+        const double resid = sqrt(acc[1]) + sqrt(acc[0]) + sqrt(acc[2]) + dm * mu;
+        if (trace != nullptr && tid == 0) {                     // what verbose=1 prints (batch.py:115-117)
+            double* tr = trace + ((int64_t)qp * maxIter + it) * 4;
+            tr[0] = sqrt(acc[1]) + sqrt(acc[0]); tr[1] = sqrt(acc[2]); tr[2] = mu; tr[3] = resid;
+        }
+        // ---- best-iterate tracking and exit tests (batch.py:118-143), per QP (see k_forward)
+        const bool improved = (it == 0) || (resid < best);
+        if (improved) { best = resid; nNot = 0; } else { ++nNot; }
+        if (improved || resid < best_tie * best) {
+            ret_resid = resid;
+            _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[FV(F_BXT) + i] = qsm[xt + i];
+            _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) { qsm[FV(F_BS) + i] = qsm[s + i]; qsm[FV(F_BV) + i] = qsm[v + i]; }
+        }
+        if ((nNot == notImprovedLim && best < stall_tol) || best < eps || mu > 1e32) break;
+        if (!(resid == resid) || isinf(resid)) break;
+        // ---- factor_kkt with d = z/s and the affine right-hand side (batch.py:109-113,150)
+        _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) {
+            double hfull = qsm[hW + i] - qsm[rv + i];
+            if (i >= ep) {
+                const double di = qsm[v + i] / qsm[s + i];
+                qsm[d + i] = di;
+                hfull += qsm[v + i] / di;
+            }
+            qsm[aug + i] = -hfull;
+        }
+        __syncthreads();
+        QPB_TICK(9);
+        f_factor_and_solve(D, C);                               // w = [dy_aff; dz_aff]
+        QPB_TICK(10);
+        // ---- affine step length and sigma (batch.py:160-168)
+        double mn[2] = {INFINITY, INFINITY};
+        _Pragma("unroll 1") for (int i = ep + tid; i < ms; i += kNT) {
+            const double dz = qsm[w + i];
+            const double dsi = (-qsm[v + i] - dz) / qsm[d + i];
+            qsm[dsa + i] = dsi;
+            mn[0] = fmin(mn[0], step_candidate(qsm[v + i], dz));
+            mn[1] = fmin(mn[1], step_candidate(qsm[s + i], dsi));
+        }
+        f_reduce_min2(mn, C.L.red);
+        {
+            const double alpha = fmin(fmin(f_step_fix(mn[0]), f_step_fix(mn[1])), 1.0);
+            double sm[2] = {0.0, 0.0};
+            _Pragma("unroll 1") for (int i = ep + tid; i < ms; i += kNT) {
+                sm[0] = fma(qsm[s + i] + alpha * qsm[dsa + i], qsm[v + i] + alpha * qsm[w + i], sm[0]);
+                sm[1] = fma(qsm[s + i], qsm[v + i], sm[1]);
+            }
+            f_reduce_sum2(sm, C.L.red);
+            const double sr = sm[0] / sm[1];
+            const double sig = sr * sr * sr;
+            // ---- corrector right-hand side (batch.py:170-181)
+            _Pragma("unroll 1") for (int i = tid; i < msp; i += kNT) {
+                double rhs = 0.0;
+                if (i >= ep && i < ms) {
+                    const double rsc = (-mu * sig + qsm[dsa + i] * qsm[w + i]) / qsm[s + i];
+                    qsm[ds + i] = rsc;
+                    rhs = -(rsc / qsm[d + i]);
+                }
+                qsm[t1 + i] = rhs;
+            }
+            __syncthreads();
+        }
+        QPB_TICK(11);
+        f_trsv_fwd(C.L.LS, D.lds, msp, 0, msp, FV(F_DINV), t1, t0);
+        QPB_TICK(12);
+        f_trsv_bwd(C.L.LS, D.lds, msp, FV(F_DINV), t0, t1);      // t1 = [dy_cor; dz_cor]
+        QPB_TICK(13);
+        f_issue_K(D, C);                                         // next factor_kkt's K copy overlaps the rest
+        // ---- combined direction, step length, update (batch.py:185-203)
+        mn[0] = INFINITY; mn[1] = INFINITY;
+        _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) {
+            const double wci = qsm[t1 + i];
+            const double dv = qsm[w + i] + wci;
+            qsm[w + i] = dv;
+            if (i >= ep) {
+                const double dsc = (-qsm[ds + i] - wci) / qsm[d + i];
+                const double dsi = qsm[dsa + i] + dsc;
+                qsm[ds + i] = dsi;
+                mn[0] = fmin(mn[0], step_candidate(qsm[v + i], dv));
+                mn[1] = fmin(mn[1], step_candidate(qsm[s + i], dsi));
+            }
+        }
+        __syncthreads();
+        QPB_TICK(14);
+        f_matvec_cols(W, ldw, ms, n, w, t0, t1, hW, rxt, -1.0, -1, -1.0);     // dx~ = -r~x - W^T dv  (in hW)
+        QPB_TICK(15);
+        f_reduce_min2(mn, C.L.red);
+        {
+            const double alpha = fmin(0.999 * fmin(f_step_fix(mn[0]), f_step_fix(mn[1])), 1.0);
+            _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[xt + i] = fma(alpha, qsm[hW + i], qsm[xt + i]);
+            _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) {
+                qsm[v + i] = fma(alpha, qsm[w + i], qsm[v + i]);
+                if (i >= ep) qsm[s + i] = fma(alpha, qsm[ds + i], qsm[s + i]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- outputs: x = L^-T x~_best, y, z, s of the returned iterate (batch.py:205-207)
+    __syncthreads();
+    QPB_TICK(16);
+    f_unwhiten(C.L.Lp, n, FV(F_DINVL), FV(F_BXT), t0);
+    if (C.kpending) f_wait_K(C);                                 // drain the in-flight copy before exit
+    _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) zhat[(int64_t)qp * n + i] = qsm[t0 + i];
+    _Pragma("unroll 1") for (int i = tid; i < m; i += kNT) {
+        lam[(int64_t)qp * m + i] = qsm[FV(F_BV) + ep + i];
+        slacks[(int64_t)qp * m + i] = qsm[FV(F_BS) + ep + i];
+    }
+    if (e > 0 && nus != nullptr)
+        _Pragma("unroll 1") for (int i = tid; i < e; i += kNT) nus[(int64_t)qp * e + i] = qsm[FV(F_BV) + i];
+    if (tid == 0) {
+        iters_out[qp] = iters_run;
+        resid_out[qp] = ret_resid;
+    }
+}
+
+template <bool kBackward>
+__global__ void __launch_bounds__(kThreads, 1)
+k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ rx_in,
+           const double* __restrict__ rs_in, const double* __restrict__ rz_in,
+           const double* __restrict__ ry_in, const double* __restrict__ zhat,
+           const double* __restrict__ lam, const double* __restrict__ slacks,
+           const double* __restrict__ nus, const double* __restrict__ Lfac,
+           const double* __restrict__ Wfac, const double* __restrict__ Kfac, int sF,
+           double* __restrict__ dx_out, double* __restrict__ ds_out, double* __restrict__ dz_out,
+           double* __restrict__ dy_out, BwdOut O) {
+    using namespace fk;
+    QPB_SMEM;
+    const int tid = threadIdx.x;
+    const int qp = blockIdx.x;
+    const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
+    FCtx C = f_make_ctx(D, qp, Lfac, Wfac, Kfac, sF);
+    const int W = C.L.W, ldw = D.ldw;
+    const int t = FV(F_PT), d = FV(F_D), hW = FV(F_HW), aug = FV(F_AUG), w = FV(F_W), t0 = FV(F_T0),
+              t1 = FV(F_T1), rsv = FV(F_S), c2 = FV(F_RV), dxt = FV(F_RXT), dxo = FV(F_XT);
+    _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[t1 + i] = rx_in[(int64_t)qp * n + i];
+    _Pragma("unroll 1") for (int i = tid; i < msp; i += kNT) {
+        double di = 1.0, extra = 0.0, rsi = 0.0;
+        if (i >= ep && i < ms) {
+            const int j = i - ep;
+            if (kBackward) {
+                di = fmax(lam[(int64_t)qp * m + j], 1e-8) / fmax(slacks[(int64_t)qp * m + j], 1e-8);   // qp.py:148
+            } else {
+                di = d_in[(int64_t)qp * m + j];
+                rsi = rs_in[(int64_t)qp * m + j];
+                extra = rsi / di - rz_in[(int64_t)qp * m + j];
+            }
+        } else if (!kBackward && i < e) {
+            extra = -ry_in[(int64_t)qp * e + i];
+        }
+        qsm[d + i] = di;
+        qsm[rsv + i] = rsi;
+        qsm[hW + i] = extra;
+        qsm[aug + i] = 0.0;
+    }
+    __syncthreads();
+    f_whiten(C.L.Lp, n, FV(F_DINVL), t1, t);                    // t = L^-1 rx
+    f_matvec_rows1(W, ldw, ms, n, t, c2);
+    __syncthreads();
+    _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) qsm[aug + i] = -(qsm[c2 + i] + qsm[hW + i]);
+    __syncthreads();
+    f_factor_and_solve(D, C);                                   // w = [dy; dz]
+    f_matvec_cols(W, ldw, ms, n, w, t0, t1, dxt, t, -1.0, -1, -1.0);
+    f_unwhiten(C.L.Lp, n, FV(F_DINVL), dxt, dxo);               // dx = L^-T dx~
+    _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) dx_out[(int64_t)qp * n + i] = qsm[dxo + i];
+    _Pragma("unroll 1") for (int i = tid; i < m; i += kNT) {
+        dz_out[(int64_t)qp * m + i] = qsm[w + ep + i];
+        if (!kBackward) ds_out[(int64_t)qp * m + i] = (-qsm[rsv + ep + i] - qsm[w + ep + i]) / qsm[d + ep + i];
+    }
+    if (e > 0 && dy_out != nullptr)
+        _Pragma("unroll 1") for (int i = tid; i < e; i += kNT) dy_out[(int64_t)qp * e + i] = qsm[w + i];
+    if (!kBackward) return;
+
+    // ---- gradients for batched inputs (qp.py:157-176); 128-bit coalesced stores
+    const int zs = FV(F_BXT), ls = FV(F_BV);
+    _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[zs + i] = zhat[(int64_t)qp * n + i];
+    _Pragma("unroll 1") for (int i = tid; i < m; i += kNT) qsm[ls + ep + i] = lam[(int64_t)qp * m + i];
+    _Pragma("unroll 1") for (int i = tid; i < e; i += kNT) qsm[ls + i] = nus[(int64_t)qp * e + i];
+    __syncthreads();
+    if (O.dp && !O.mp) for (int i = tid; i < n; i += kNT) O.dp[(int64_t)qp * n + i] = qsm[dxo + i];
+    if (O.dh && !O.mh) for (int i = tid; i < m; i += kNT) O.dh[(int64_t)qp * m + i] = -qsm[w + ep + i];
+    if (O.db && !O.mb && e > 0) for (int i = tid; i < e; i += kNT) O.db[(int64_t)qp * e + i] = -qsm[w + i];
+    const bool even = (n & 1) == 0;
+    if (O.dQ && !O.mQ) {
+        double* o = O.dQ + (int64_t)qp * n * n;
+        if (even) {
+            const int n2 = n >> 1;
+            _Pragma("unroll 1") for (int i = tid; i < n * n2; i += kNT) {
+                const int r = i / n2, c = (i - r * n2) * 2;
+                const double dr = qsm[dxo + r], zr = qsm[zs + r];
+                reinterpret_cast<double2*>(o)[i] = make_double2(0.5 * (dr * qsm[zs + c] + zr * qsm[dxo + c]),
+                                                                0.5 * (dr * qsm[zs + c + 1] + zr * qsm[dxo + c + 1]));
+            }
+        } else {
+            _Pragma("unroll 1") for (int i = tid; i < n * n; i += kNT) {
+                const int r = i / n, c = i - r * n;
+                o[i] = 0.5 * (qsm[dxo + r] * qsm[zs + c] + qsm[zs + r] * qsm[dxo + c]);
+            }
+        }
+    }
+    if (O.dG && !O.mG) {
+        double* o = O.dG + (int64_t)qp * m * n;
+        if (even) {
+            const int n2 = n >> 1;
+            _Pragma("unroll 1") for (int i = tid; i < m * n2; i += kNT) {
+                const int r = i / n2, c = (i - r * n2) * 2;
+                const double wr = qsm[w + ep + r], lr = qsm[ls + ep + r];
+                reinterpret_cast<double2*>(o)[i] = make_double2(wr * qsm[zs + c] + lr * qsm[dxo + c],
+                                                                wr * qsm[zs + c + 1] + lr * qsm[dxo + c + 1]);
+            }
+        } else {
+            _Pragma("unroll 1") for (int i = tid; i < m * n; i += kNT) {
+                const int r = i / n, c = i - r * n;
+                o[i] = qsm[w + ep + r] * qsm[zs + c] + qsm[ls + ep + r] * qsm[dxo + c];
+            }
+        }
+    }
+    if (O.dA && !O.mA && e > 0) {
+        double* o = O.dA + (int64_t)qp * e * n;
+        _Pragma("unroll 1") for (int i = tid; i < e * n; i += kNT) {
+            const int r = i / n, c = i - r * n;
+            o[i] = qsm[w + r] * qsm[zs + c] + qsm[ls + r] * qsm[dxo + c];
+        }
+    }
+}
+
 // fp64 FMA issue-rate probe: 8 independent DFMA chains per thread (roofline denominator for bench.py)
 __global__ void k_dfma_probe(int iters, double* out) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
@@ -660,7 +1122,7 @@ int cuda_fail(cudaError_t err, const char* what) {
 
 KDims dims_of(const qpb200_plan* p) {
     KDims D;
-    D.n = p->nz; D.m = p->nineq; D.e = p->neq; D.ep = p->neq_pad; D.ms = p->ms;
+    D.n = p->nz; D.m = p->nineq; D.e = p->neq; D.ep = p->neq_pad; D.ms = p->ms; D.msp = p->ms_pad;
     D.ldw = p->ldw; D.lds = p->lds; D.rows_s = p->rows_s; D.vl = p->vl;
     D.lp = (int)p->L_elems;
     return D;
@@ -699,16 +1161,16 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
     plan->nz = nz; plan->nineq = nineq; plan->neq = neq;
     plan->neq_pad = (neq + 7) & ~7;
     plan->ms = plan->neq_pad + nineq;
-    const int ms = plan->ms;
+    plan->ms_pad = (plan->ms + 7) & ~7;
+    const int ms = plan->ms, msp = plan->ms_pad;
     plan->ldw = ld_for(nz);
-    plan->lds = ld_for(nz > ms ? nz : ms);
-    plan->rows_s = (nz > ms + 1) ? nz : (ms + 1);
-    int vl = (nz > ms ? nz : ms) + 8;
-    plan->vl = (vl + 7) & ~7;
+    plan->lds = ld_for(msp);
+    plan->rows_s = msp;
+    plan->vl = (((nz > msp ? nz : msp) + 8) + 7) & ~7;
     plan->threads = kThreads;
     plan->L_elems = (((int64_t)nz * (nz + 1)) / 2 + 1) & ~(int64_t)1;   // packed lower, even count
     plan->W_elems = (int64_t)ms * plan->ldw;
-    plan->K_elems = (int64_t)ms * plan->lds;
+    plan->K_elems = (int64_t)msp * plan->lds;
     const int ldn = ld_for(nz), ldk = ld_for(ms);
     const int64_t regA = (int64_t)nz * ldn > (int64_t)ms * ldk ? (int64_t)nz * ldn : (int64_t)ms * ldk;
     const int64_t setup_mat = regA + (int64_t)ms * ldn;
@@ -716,11 +1178,16 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
     const int64_t solve_mat_s = (int64_t)ms * plan->ldw + (int64_t)plan->rows_s * plan->lds + plan->L_elems;
     const int64_t solve_mat = (int64_t)plan->rows_s * plan->lds;     // global mode: only the S workspace
     const int64_t solve_vec = (int64_t)solve_vec_doubles(plan->vl);
-    const bool fits = (solve_mat_s + solve_vec) * 8 <= kMaxSmem && (setup_mat + setup_vec) * 8 <= kMaxSmem;
-    plan->smem_resident = fits ? 1 : 0;
-    if (fits) {
+    KDims D = dims_of(plan);
+    const int64_t fast_doubles = (int64_t)fk::fast_smem_doubles(D);
+    const bool setup_fits = (setup_mat + setup_vec) * 8 <= kMaxSmem;
+    const bool fast_ok = setup_fits && fast_doubles * 8 <= kMaxSmem && nineq <= 8 * kCholMaxTiles && (msp - plan->neq_pad) / 8 >= 1;
+    const bool fits = setup_fits && (solve_mat_s + solve_vec) * 8 <= kMaxSmem;
+    plan->fast = fast_ok ? 1 : 0;
+    plan->smem_resident = (fast_ok || fits) ? 1 : 0;
+    if (setup_fits && (fast_ok || fits)) {
         plan->setup_smem_bytes = (setup_mat + setup_vec) * 8;
-        plan->solve_smem_bytes = (solve_mat_s + solve_vec) * 8;
+        plan->solve_smem_bytes = fast_ok ? fast_doubles * 8 : (solve_mat_s + solve_vec) * 8;
         plan->setup_scratch_elems = 0;
         plan->solve_scratch_elems = 0;
     } else {
@@ -769,20 +1236,27 @@ int qpb200_forward(const qpb200_plan* plan, int nbatch, const double* p, int64_t
     if (plan->neq > 0 && (!b || !nus)) return QPB200_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     KDims D = dims_of(plan);
-    if (plan->smem_resident) {
-        int rc = set_smem(k_forward<true>, plan->solve_smem_bytes);
+#define QPB_LAUNCH_FWD(KS, KV, SCR, SCRN)                                                              \
+    do {                                                                                                \
+        int rc = set_smem(k_forward<KS, KV>, plan->solve_smem_bytes);                                   \
+        if (rc) return rc;                                                                              \
+        k_forward<KS, KV><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(                            \
+            D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim,     \
+            maxIter, zhat, lam, slacks, nus, iters, best_resid, trace, SCR, SCRN);                      \
+    } while (0)
+    if (plan->fast) {
+        int rc = set_smem(k_forward_fast, plan->solve_smem_bytes);
         if (rc) return rc;
-        k_forward<true><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
-            D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, maxIter, zhat, lam,
-            slacks, nus, iters, best_resid, trace, nullptr, 0);
+        k_forward_fast<<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
+            D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, maxIter,
+            zhat, lam, slacks, nus, iters, best_resid, trace);
+    } else if (plan->smem_resident) {
+        QPB_LAUNCH_FWD(true, false, nullptr, 0);
     } else {
         if (!scratch) return QPB200_ERR_BAD_ARG;
-        int rc = set_smem(k_forward<false>, plan->solve_smem_bytes);
-        if (rc) return rc;
-        k_forward<false><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
-            D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, maxIter, zhat, lam,
-            slacks, nus, iters, best_resid, trace, scratch, plan->solve_scratch_elems);
+        QPB_LAUNCH_FWD(false, false, scratch, plan->solve_scratch_elems);
     }
+#undef QPB_LAUNCH_FWD
     CK(cudaGetLastError());
     return QPB200_OK;
 }
@@ -798,20 +1272,26 @@ int qpb200_solve_kkt(const qpb200_plan* plan, int nbatch, const double* d, const
     KDims D = dims_of(plan);
     BwdOut O;
     memset(&O, 0, sizeof(O));
-    if (plan->smem_resident) {
-        int rc = set_smem(k_solve_kkt<true, false>, plan->solve_smem_bytes);
+#define QPB_LAUNCH_KKT(KS, KV, SCR, SCRN)                                                              \
+    do {                                                                                                \
+        int rc = set_smem(k_solve_kkt<KS, KV, false>, plan->solve_smem_bytes);                          \
+        if (rc) return rc;                                                                              \
+        k_solve_kkt<KS, KV, false><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(                   \
+            D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz, \
+            dy, O, SCR, SCRN);                                                                          \
+    } while (0)
+    if (plan->fast) {
+        int rc = set_smem(k_kkt_fast<false>, plan->solve_smem_bytes);
         if (rc) return rc;
-        k_solve_kkt<true, false><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
-            D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz,
-            dy, O, nullptr, 0);
+        k_kkt_fast<false><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
+            D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz, dy, O);
+    } else if (plan->smem_resident) {
+        QPB_LAUNCH_KKT(true, false, nullptr, 0);
     } else {
         if (!scratch) return QPB200_ERR_BAD_ARG;
-        int rc = set_smem(k_solve_kkt<false, false>, plan->solve_smem_bytes);
-        if (rc) return rc;
-        k_solve_kkt<false, false><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
-            D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz,
-            dy, O, scratch, plan->solve_scratch_elems);
+        QPB_LAUNCH_KKT(false, false, scratch, plan->solve_scratch_elems);
     }
+#undef QPB_LAUNCH_KKT
     CK(cudaGetLastError());
     return QPB200_OK;
 }
@@ -832,20 +1312,27 @@ int qpb200_backward(const qpb200_plan* plan, int nbatch, const double* dl_dzhat,
     BwdOut O;
     O.dQ = dQ; O.dp = dp; O.dG = dG; O.dh = dh; O.dA = dA; O.db = db;
     O.mQ = mean_Q; O.mp = mean_p; O.mG = mean_G; O.mh = mean_h; O.mA = mean_A; O.mb = mean_b;
-    if (plan->smem_resident) {
-        int rc = set_smem(k_solve_kkt<true, true>, plan->solve_smem_bytes);
+#define QPB_LAUNCH_BWD(KS, KV, SCR, SCRN)                                                              \
+    do {                                                                                                \
+        int rc = set_smem(k_solve_kkt<KS, KV, true>, plan->solve_smem_bytes);                           \
+        if (rc) return rc;                                                                              \
+        k_solve_kkt<KS, KV, true><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(                    \
+            D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac,  \
+            sF, dxv, nullptr, dlamv, dnuv, O, SCR, SCRN);                                               \
+    } while (0)
+    if (plan->fast) {
+        int rc = set_smem(k_kkt_fast<true>, plan->solve_smem_bytes);
         if (rc) return rc;
-        k_solve_kkt<true, true><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
-            D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac,
-            sF, dxv, nullptr, dlamv, dnuv, O, nullptr, 0);
+        k_kkt_fast<true><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
+            D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac, sF, dxv,
+            nullptr, dlamv, dnuv, O);
+    } else if (plan->smem_resident) {
+        QPB_LAUNCH_BWD(true, false, nullptr, 0);
     } else {
         if (!scratch) return QPB200_ERR_BAD_ARG;
-        int rc = set_smem(k_solve_kkt<false, true>, plan->solve_smem_bytes);
-        if (rc) return rc;
-        k_solve_kkt<false, true><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
-            D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac,
-            sF, dxv, nullptr, dlamv, dnuv, O, scratch, plan->solve_scratch_elems);
+        QPB_LAUNCH_BWD(false, false, scratch, plan->solve_scratch_elems);
     }
+#undef QPB_LAUNCH_BWD
     CK(cudaGetLastError());
     const int TB = 256;
     if (dQ && mean_Q)
@@ -862,6 +1349,18 @@ int qpb200_backward(const qpb200_plan* plan, int nbatch, const double* dl_dzhat,
     CK(cudaGetLastError());
     return QPB200_OK;
 }
+
+#ifdef QPB_TIMING
+int qpb200_debug_timing(long long* host64, int reset) {
+    if (reset) {
+        long long z[64] = {0};
+        CK(cudaMemcpyToSymbol(qpb::fast::g_tim, z, sizeof(z)));
+        return QPB200_OK;
+    }
+    CK(cudaMemcpyFromSymbol(host64, qpb::fast::g_tim, 64 * sizeof(long long)));
+    return QPB200_OK;
+}
+#endif
 
 int qpb200_dfma_probe(int blocks, int threads, int iters, double* out, void* stream) {
     if (blocks <= 0 || threads <= 0 || iters <= 0 || !out) return QPB200_ERR_BAD_ARG;

@@ -1,0 +1,31 @@
+"""Cycle accounting of k_forward_fast phases (needs libqpth_b200_timing.so built with -DQPB_TIMING)."""
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from qpth_b200 import _lib
+_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libqpth_b200_timing.so")
+from qpth_b200 import QPFunction
+from qpth_b200.problems import random_qp_batch
+B, n, m, e = [int(x) for x in (sys.argv[1:5] if len(sys.argv) > 4 else (128, 100, 100, 0))]
+lib = _lib.load()
+lib.qpb200_debug_timing.restype = ctypes.c_int
+lib.qpb200_debug_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]
+pr = random_qp_batch(B, n, m, e, seed=0)
+dev = "cuda:0"
+t = {k: (torch.tensor(v, dtype=torch.float64, device=dev) if v.size else torch.Tensor().to(dev).double()) for k, v in pr.items() if k != "dl"}
+f = QPFunction(verbose=-1, check_Q_spd=False)
+f(t["Q"], t["p"], t["G"], t["h"], t["A"], t["b"]); torch.cuda.synchronize()
+lib.qpb200_debug_timing(None, 1)
+f(t["Q"], t["p"], t["G"], t["h"], t["A"], t["b"]); torch.cuda.synchronize()
+buf = (ctypes.c_longlong * 64)()
+lib.qpb200_debug_timing(buf, 0)
+it = int(f.last_solve().iters[0])
+names = {0: "make_ctx (TMA W,L)", 1: "load vectors", 2: "whiten", 3: "loop misc/update (prev)", 4: "matvec_cols (r~x)", 5: "matvec_rows2", 6: "residual elementwise", 7: "tri_norm2", 8: "reduce_sum4",
+         9: "best/exit/aug build", 10: "factor_and_solve tail", 11: "aff step, sigma, rhs", 12: "trsv_fwd (cor)", 13: "trsv_bwd (cor)", 14: "issue_K + combine", 15: "matvec_cols (dx)", 16: "final misc",
+         20: "chol: tile load + first factor", 21: "chol: first barrier", 22: "chol: phase A work", 23: "chol: barrier after A", 24: "chol: diag tile update+publish", 25: "chol: factor_diag8", 26: "chol: other diag tiles", 27: "chol: barrier after B",
+         30: "wait K copy", 31: "diag add + barrier", 32: "chol exit", 33: "trsv_bwd (aff)"}
+tot = sum(buf)
+print("QP 0 of block 0: %d iterations; total %d cycles (%.1f us @1.965GHz); per iteration %.0f" % (it, tot, tot / 1965.0, tot / (it + 1)))
+for i in range(64):
+    if buf[i]:
+        print("%2d %-34s %9d cyc  %5.1f%%   per-iter %7.0f" % (i, names.get(i, "?"), buf[i], 100.0 * buf[i] / tot, buf[i] / (it + 1)))

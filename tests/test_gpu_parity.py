@@ -169,7 +169,7 @@ def test_pre_factor_blocks_match_definition():
     Q, G, A = tt(pr["Q"]), tt(pr["G"]), tt(pr["A"])
     L = torch.empty(B, plan.L_elems, dtype=torch.float64, device=DEV)
     W = torch.empty(B, plan.ms, plan.ldw, dtype=torch.float64, device=DEV)
-    K = torch.empty(B, plan.ms, plan.lds, dtype=torch.float64, device=DEV)
+    K = torch.empty(B, plan.ms_pad, plan.lds, dtype=torch.float64, device=DEV)
     spd = torch.zeros(B, dtype=torch.int32, device=DEV)
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -187,7 +187,7 @@ def test_pre_factor_blocks_match_definition():
         assert np.abs(Wn[i][e:ep]).max() == 0.0
         assert np.abs(Wn[i][ep:] - Wref[e:]).max() < 1e-8 * np.abs(Wref).max()
         F = orc.Factors(pr["Q"][i:i + 1], pr["G"][i:i + 1], pr["A"][i:i + 1])
-        Rk = np.tril(Kn[i][ep:, ep:])
+        Rk = np.tril(Kn[i][ep:plan.ms, ep:])
         assert np.abs(Rk - np.tril(F.R[0])).max() < 1e-8 * np.abs(F.R[0]).max()
 
 
