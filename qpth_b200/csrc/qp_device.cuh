@@ -336,7 +336,7 @@ __device__ __forceinline__ void chol_partial(double* A, int ld, int nsq, int c0,
 // T = L_kk^-1 transposed into the (otherwise unused) upper part of its diagonal block.
 // =============================================================================================
 constexpr int kCholMaxTiles = 13;       // tile rows supported by chol_v2 (order <= 104)
-constexpr int kCholMaxOff = 12;         // off-diagonal tiles per update warp: ceil(78 / 7)
+constexpr int kCholMaxOff = 13;         // off-diagonal tiles per update warp (6 or 7 update warps)
 
 // Factor the 8x8 diagonal block at (k0,k0) (nb valid rows/cols) redundantly in every lane of one warp,
 // invert it, and write L (lower), T^T (upper) and dinv.

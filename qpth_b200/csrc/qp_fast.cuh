@@ -21,13 +21,14 @@ namespace fast {
 // phase into g_tim[]; read back with qpb200_debug_timing(). Compiled out of the product build.
 #ifdef QPB_TIMING
 __device__ long long g_tim[64];
-__device__ long long g_tlast;
+// accumulators live in (static) shared memory so that a tick costs ~40 cycles, not a global round trip
+__shared__ long long s_tim[65];
 #define QPB_TICK(i)                                                         \
     do {                                                                    \
-        if (threadIdx.x == 0 && blockIdx.x == 0) {                          \
+        if (threadIdx.x == 0) {                                             \
             const long long _t = clock64();                                 \
-            g_tim[i] += _t - g_tlast;                                       \
-            g_tlast = _t;                                                   \
+            s_tim[i] += _t - s_tim[64];                                     \
+            s_tim[64] = _t;                                                 \
         }                                                                   \
     } while (0)
 #else
@@ -37,22 +38,32 @@ __device__ long long g_tlast;
 constexpr int kNT = 256;
 
 // ---- 8x8 diagonal block helpers (always full blocks here) -------------------------------------------
-// Factor the block at (k0,k0) of the matrix at offset A (ld), invert it, write L (lower), T^T (upper), dinv.
-__device__ __noinline__ void f_factor_diag8(int A, int ld, int k0, int dinv) {
-    QPB_SMEM;
-    const int lane = threadIdx.x & 31;
-    double* M = qsm + A + k0 * ld + k0;
-    double Lk[36], T[36], rinv[8];
+// Storage convention of a factored diagonal block: strictly-lower part = L, DIAGONAL = 1 / L_cc.
+// (Nothing downstream needs L_cc itself; every use is a multiplication by its reciprocal.)
+
+// Load the lower triangle (incl. diagonal) of the 8x8 block at Mb with 128-bit loads (20 LDS.128).
+__device__ __forceinline__ void f_load_lower8(const double* Mb, int ld, double (&Lk)[36]) {
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int c = 0; c <= r; ++c) Lk[QPB_LIDX(r, c)] = M[r * ld + c];
+        for (int c = 0; c <= r; c += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(Mb + r * ld + c);
+            Lk[QPB_LIDX(r, c)] = v.x;
+            if (c + 1 <= r) Lk[QPB_LIDX(r, c + 1)] = v.y;
+        }
+}
+
+// Factor the 8x8 block at Mb redundantly in every lane of the calling warp; lane 0 writes it back
+// (strictly lower = L, diagonal = rsqrt(pivot)).
+__device__ __noinline__ void f_factor8(int Mb_off, int ld) {
+    QPB_SMEM;
+    double* Mb = qsm + Mb_off;
+    double Lk[36];
+    f_load_lower8(Mb, ld, Lk);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const double piv = Lk[QPB_LIDX(c, c)];
-        const double ri = rsqrt(piv);
-        rinv[c] = ri;
-        Lk[QPB_LIDX(c, c)] = piv * ri;
+        const double ri = rsqrt(Lk[QPB_LIDX(c, c)]);
+        Lk[QPB_LIDX(c, c)] = ri;
 #pragma unroll
         for (int r = c + 1; r < 8; ++r) Lk[QPB_LIDX(r, c)] *= ri;
 #pragma unroll
@@ -61,45 +72,43 @@ __device__ __noinline__ void f_factor_diag8(int A, int ld, int k0, int dinv) {
             for (int cc = c + 1; cc <= r; ++cc)
                 Lk[QPB_LIDX(r, cc)] = fma(-Lk[QPB_LIDX(r, c)], Lk[QPB_LIDX(cc, c)], Lk[QPB_LIDX(r, cc)]);
     }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        T[QPB_LIDX(c, c)] = rinv[c];
-#pragma unroll
-        for (int r = c + 1; r < 8; ++r) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int j = c; j < r; ++j) sacc = fma(Lk[QPB_LIDX(r, j)], T[QPB_LIDX(j, c)], sacc);
-            T[QPB_LIDX(r, c)] = -rinv[r] * sacc;
-        }
-    }
-    if (lane == 0) {        // one divergent region instead of 72 predicated stores (those compiled to 72 branches)
+    if ((threadIdx.x & 31) == 0) {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int c = 0; c <= r; ++c) M[r * ld + c] = Lk[QPB_LIDX(r, c)];
-#pragma unroll
-        for (int r = 1; r < 8; ++r)
-#pragma unroll
-            for (int c = 0; c < r; ++c) M[c * ld + r] = T[QPB_LIDX(r, c)];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) qsm[dinv + k0 + c] = rinv[c];
+            for (int c = 0; c <= r; c += 2)      // the odd tail writes one element of the (unused) upper part
+                *reinterpret_cast<double2*>(Mb + r * ld + c) =
+                    make_double2(Lk[QPB_LIDX(r, c)], (c + 1 <= r) ? Lk[QPB_LIDX(r, c + 1)] : 0.0);
     }
     __syncwarp();
 }
 
-// T = L_kk^-1 from its transposed home in the upper triangle of the diagonal block.
-__device__ __forceinline__ void f_load_T8(const double* M, int ld, const double* dv, double (&T)[36]) {
+// a <- a * L_kk^-T by substitution (Lk: strictly lower = L, diagonal = reciprocal).
+__device__ __forceinline__ void f_row_solve8(double (&a)[8], const double (&Lk)[36]) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        T[QPB_LIDX(r, r)] = dv[r];
+    for (int c = 0; c < 8; ++c) {
+        a[c] *= Lk[QPB_LIDX(c, c)];
 #pragma unroll
-        for (int c = 0; c < r; ++c) T[QPB_LIDX(r, c)] = M[c * ld + r];
+        for (int c2 = c + 1; c2 < 8; ++c2) a[c2] = fma(-a[c], Lk[QPB_LIDX(c2, c)], a[c2]);
     }
 }
 
-// ---- Cholesky with register-resident trailing matrix and look-ahead (see chol_v2 in qp_device.cuh) ----
-// n is a multiple of 8, (n - c0)/8 <= 13, blockDim.x == 256. aug (offset) is the right-hand side, length n.
-__device__ __noinline__ void f_chol(int A, int ld, int n, int c0, int aug, int dinv, int tabo) {
+__device__ __forceinline__ void f_ld8(const double* p, double (&a)[8]) {
+    const double2 v0 = *reinterpret_cast<const double2*>(p), v1 = *reinterpret_cast<const double2*>(p + 2),
+                  v2 = *reinterpret_cast<const double2*>(p + 4), v3 = *reinterpret_cast<const double2*>(p + 6);
+    a[0] = v0.x; a[1] = v0.y; a[2] = v1.x; a[3] = v1.y; a[4] = v2.x; a[5] = v2.y; a[6] = v3.x; a[7] = v3.y;
+}
+__device__ __forceinline__ void f_st8(double* p, const double (&a)[8]) {
+    *reinterpret_cast<double2*>(p) = make_double2(a[0], a[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(a[2], a[3]);
+    *reinterpret_cast<double2*>(p + 4) = make_double2(a[4], a[5]);
+    *reinterpret_cast<double2*>(p + 6) = make_double2(a[6], a[7]);
+}
+
+// ---- Cholesky: register-resident off-diagonal tiles (warps 1..7), look-ahead on warp 0 ------------------
+// n multiple of 8, (n - c0)/8 <= 13, blockDim.x == 256. aug (offset) = right-hand side (length n) carried
+// along so that L^-1 aug falls out of the factorization. Diagonal blocks end up in the convention above.
+__device__ __noinline__ void f_chol(int A, int ld, int n, int c0, int aug, int tabo) {
     QPB_SMEM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -107,20 +116,16 @@ __device__ __noinline__ void f_chol(int A, int ld, int n, int c0, int aug, int d
     const int noff = (nts * (nts - 1)) / 2;
     const uint16_t* tab = reinterpret_cast<const uint16_t*>(qsm + tabo);
     double* M = qsm + A;
-    double C[kCholMaxTiles][2];
+    // update warps: 1,2,3,5,6,7 -> uw = 0..5. Warp 4 shares its scheduler (and fp64 pipe) with the critical
+    // warp 0, so it takes no DMMA work: the factor chain on warp 0 then runs uncontended.
+    const int uw = (warp == 0 || warp == 4) ? -1 : (warp < 4 ? warp - 1 : warp - 2);
+    double C[kCholMaxOff][2];
     if (warp == 0) {
-#pragma unroll
-        for (int s = 0; s < kCholMaxTiles; ++s) {
-            const bool ok = s < nts;
-            const double2 v = ok ? *reinterpret_cast<const double2*>(M + (c0 + 8 * s + g) * ld + c0 + 8 * s + 2 * q)
-                                 : make_double2(0.0, 0.0);
-            C[s][0] = v.x; C[s][1] = v.y;
-        }
-        f_factor_diag8(A, ld, c0, dinv);
-    } else {
+        f_factor8(A + c0 * ld + c0, ld);
+    } else if (uw >= 0) {
 #pragma unroll
         for (int s = 0; s < kCholMaxOff; ++s) {
-            const int idx = s * 7 + warp - 1;
+            const int idx = s * 6 + uw;
             const bool ok = idx < noff;
             const int tt = ok ? tab[idx] : 0;
             const double2 v = ok ? *reinterpret_cast<const double2*>(M + (c0 + 8 * (tt >> 8) + g) * ld + c0 + 8 * (tt & 255) + 2 * q)
@@ -128,68 +133,45 @@ __device__ __noinline__ void f_chol(int A, int ld, int n, int c0, int aug, int d
             C[s][0] = v.x; C[s][1] = v.y;
         }
     }
-    QPB_TICK(20);   // tile load + first factor
+    QPB_TICK(20);
     __syncthreads();
     QPB_TICK(21);
     for (int k = 0; k < nts; ++k) {
         const int k0 = c0 + 8 * k;
-        // ---- phase A: rows below the diagonal block (and the aug row) times T^T
+        // ---- phase A: rows below the diagonal block (and the aug row): row <- row * L_kk^-T
         {
             const int nbelow = n - k0 - 8;
             if (tid <= nbelow) {
-                double T[36], a[8];
-                f_load_T8(M + k0 * ld + k0, ld, qsm + dinv + k0, T);
+                double Lk[36], a[8];
                 double* rowp = (tid < nbelow) ? (M + (k0 + 8 + tid) * ld + k0) : (qsm + aug + k0);
-                const double2 v0 = *reinterpret_cast<const double2*>(rowp), v1 = *reinterpret_cast<const double2*>(rowp + 2),
-                              v2 = *reinterpret_cast<const double2*>(rowp + 4), v3 = *reinterpret_cast<const double2*>(rowp + 6);
-                a[0] = v0.x; a[1] = v0.y; a[2] = v1.x; a[3] = v1.y; a[4] = v2.x; a[5] = v2.y; a[6] = v3.x; a[7] = v3.y;
-                double o[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    double acc = a[c] * T[QPB_LIDX(c, c)];
-#pragma unroll
-                    for (int j = 0; j < c; ++j) acc = fma(a[j], T[QPB_LIDX(c, j)], acc);
-                    o[c] = acc;
-                }
-                *reinterpret_cast<double2*>(rowp) = make_double2(o[0], o[1]);
-                *reinterpret_cast<double2*>(rowp + 2) = make_double2(o[2], o[3]);
-                *reinterpret_cast<double2*>(rowp + 4) = make_double2(o[4], o[5]);
-                *reinterpret_cast<double2*>(rowp + 6) = make_double2(o[6], o[7]);
+                f_ld8(rowp, a);
+                f_load_lower8(M + k0 * ld + k0, ld, Lk);
+                f_row_solve8(a, Lk);
+                f_st8(rowp, a);
             }
         }
-        QPB_TICK(22);   // phase A work (thread 0)
+        QPB_TICK(22);
         __syncthreads();
-        QPB_TICK(23);   // barrier after A
+        QPB_TICK(23);
         if (k + 1 >= nts) break;
-        // ---- phase B: trailing update from registers; warp 0 looks ahead (diag tile k+1 -> factor)
+        // ---- phase B: trailing update with panel k
         if (warp == 0) {
-#pragma unroll
-            for (int s = 1; s < kCholMaxTiles; ++s) {
-                if (s == k + 1) {
-                    const double* pr = M + (c0 + 8 * s + g) * ld + k0 + q;
-                    const double a0 = pr[0], a1 = pr[4];
-                    dmma884(C[s][0], C[s][1], -a0, a0);
-                    dmma884(C[s][0], C[s][1], -a1, a1);
-                    *reinterpret_cast<double2*>(M + (c0 + 8 * s + g) * ld + c0 + 8 * s + 2 * q) = make_double2(C[s][0], C[s][1]);
-                }
-            }
+            // look-ahead: bring diagonal tile k+1 up to date (it lives in shared memory) and factor it
+            double* pd = M + (k0 + 8 + g) * ld + k0 + 8 + 2 * q;
+            const double* pr = M + (k0 + 8 + g) * ld + k0 + q;
+            double2 cv = *reinterpret_cast<const double2*>(pd);
+            const double a0 = pr[0], a1 = pr[4];
+            dmma884(cv.x, cv.y, -a0, a0);
+            dmma884(cv.x, cv.y, -a1, a1);
+            *reinterpret_cast<double2*>(pd) = cv;
             __syncwarp();
-            QPB_TICK(24);   // diag tile update + publish
-            f_factor_diag8(A, ld, k0 + 8, dinv);
-            QPB_TICK(25);   // factor + invert 8x8
-#pragma unroll
-            for (int s = 2; s < kCholMaxTiles; ++s) {
-                if (s > k + 1 && s < nts) {
-                    const double* pr = M + (c0 + 8 * s + g) * ld + k0 + q;
-                    const double a0 = pr[0], a1 = pr[4];
-                    dmma884(C[s][0], C[s][1], -a0, a0);
-                    dmma884(C[s][0], C[s][1], -a1, a1);
-                }
-            }
-        } else {
+            QPB_TICK(24);
+            f_factor8(A + (k0 + 8) * ld + k0 + 8, ld);
+            QPB_TICK(25);
+        } else if (uw >= 0) {
 #pragma unroll
             for (int s = 0; s < kCholMaxOff; ++s) {
-                const int idx = s * 7 + warp - 1;
+                const int idx = s * 6 + uw;
                 if (idx < noff) {
                     const int tt = tab[idx];
                     const int ti = tt >> 8, tj = tt & 255;
@@ -205,90 +187,90 @@ __device__ __noinline__ void f_chol(int A, int ld, int n, int c0, int aug, int d
                     }
                 }
             }
+            // remaining diagonal tiles (s > k+1) are updated in place in shared memory, spread over warps 1..7
+            for (int s = k + 2 + uw; s < nts; s += 6) {
+                double* pd = M + (c0 + 8 * s + g) * ld + c0 + 8 * s + 2 * q;
+                const double* pr = M + (c0 + 8 * s + g) * ld + k0 + q;
+                double2 cv = *reinterpret_cast<const double2*>(pd);
+                const double a0 = pr[0], a1 = pr[4];
+                dmma884(cv.x, cv.y, -a0, a0);
+                dmma884(cv.x, cv.y, -a1, a1);
+                *reinterpret_cast<double2*>(pd) = cv;
+            }
             if (warp == 7) {                    // right-hand side: aug[j] -= P[j][:] . y
                 double y[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) y[c] = qsm[aug + k0 + c];
+                f_ld8(qsm + aug + k0, y);
                 for (int j = k0 + 8 + lane; j < n; j += 32) {
-                    const double* pr = M + j * ld + k0;
-                    double acc = qsm[aug + j];
+                    double pr[8];
+                    f_ld8(M + j * ld + k0, pr);
+                    double acc0 = qsm[aug + j], acc1 = 0.0;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) acc = fma(-pr[c], y[c], acc);
-                    qsm[aug + j] = acc;
+                    for (int c = 0; c < 8; c += 2) { acc0 = fma(-pr[c], y[c], acc0); acc1 = fma(-pr[c + 1], y[c + 1], acc1); }
+                    qsm[aug + j] = acc0 + acc1;
                 }
             }
         }
-        QPB_TICK(26);       // remaining diag tiles (warp 0)
+        QPB_TICK(26);
         __syncthreads();
-        QPB_TICK(27);       // barrier after B
+        QPB_TICK(27);
     }
 }
 
-// ---- triangular solves with the inverted diagonal blocks (full 8-blocks, n multiple of 8) ----------------
+// ---- triangular solves by substitution on 8-blocks (n multiple of 8) --------------------------------------
 // Forward over blocks [kbeg, kend): u[k] = solution entries; b[i >= kend] updated. b destroyed. b != u.
-__device__ __noinline__ void f_trsv_fwd(int A, int ld, int n, int kbeg, int kend, int dinv, int b, int u) {
+__device__ __noinline__ void f_trsv_fwd(int A, int ld, int n, int kbeg, int kend, int b, int u) {
     QPB_SMEM;
     const int tid = threadIdx.x;
     const double* M = qsm + A;
     for (int k0 = kbeg; k0 < kend; k0 += 8) {
         const int nbelow = n - k0 - 8;
         if (tid < nbelow || tid == 0) {
-            double T[36], y[8];
-            f_load_T8(M + k0 * ld + k0, ld, qsm + dinv + k0, T);
-            double r[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) r[c] = qsm[b + k0 + c];
+            double Lk[36], y[8], row[8];
+            const bool has = tid < nbelow;
+            f_ld8(qsm + b + k0, y);
+            if (has) f_ld8(M + (k0 + 8 + tid) * ld + k0, row);
+            f_load_lower8(M + k0 * ld + k0, ld, Lk);
+            double acc0 = has ? qsm[b + k0 + 8 + tid] : 0.0, acc1 = 0.0;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                double acc = r[c] * T[QPB_LIDX(c, c)];
+                y[c] *= Lk[QPB_LIDX(c, c)];
 #pragma unroll
-                for (int j = 0; j < c; ++j) acc = fma(r[j], T[QPB_LIDX(c, j)], acc);
-                y[c] = acc;
+                for (int c2 = c + 1; c2 < 8; ++c2) y[c2] = fma(-y[c], Lk[QPB_LIDX(c2, c)], y[c2]);
+                if (has) { if (c & 1) acc1 = fma(-row[c], y[c], acc1); else acc0 = fma(-row[c], y[c], acc0); }
             }
-            if (tid == 0) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) qsm[u + k0 + c] = y[c];
-            }
-            if (tid < nbelow) {
-                const double* rowp = M + (k0 + 8 + tid) * ld + k0;
-                double acc = qsm[b + k0 + 8 + tid];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) acc = fma(-rowp[c], y[c], acc);
-                qsm[b + k0 + 8 + tid] = acc;
-            }
+            if (tid == 0) f_st8(qsm + u + k0, y);
+            if (has) qsm[b + k0 + 8 + tid] = acc0 + acc1;
         }
         __syncthreads();
     }
 }
 
 // Backward: L^T w = u over all blocks. u destroyed. u != w.
-__device__ __noinline__ void f_trsv_bwd(int A, int ld, int n, int dinv, int u, int w) {
+__device__ __noinline__ void f_trsv_bwd(int A, int ld, int n, int u, int w) {
     QPB_SMEM;
     const int tid = threadIdx.x;
     const double* M = qsm + A;
     for (int k0 = n - 8; k0 >= 0; k0 -= 8) {
         if (tid < k0 || tid == 0) {
-            double T[36], y[8], r[8];
-            f_load_T8(M + k0 * ld + k0, ld, qsm + dinv + k0, T);
+            double Lk[36], y[8];
+            const bool has = tid < k0;
+            f_ld8(qsm + u + k0, y);
+            double col[8];
+            if (has) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) r[c] = qsm[u + k0 + c];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {                       // y = T^T r
-                double acc = r[c] * T[QPB_LIDX(c, c)];
-#pragma unroll
-                for (int j = c + 1; j < 8; ++j) acc = fma(r[j], T[QPB_LIDX(j, c)], acc);
-                y[c] = acc;
+                for (int c = 0; c < 8; ++c) col[c] = M[(k0 + c) * ld + tid];
             }
-            if (tid == 0) {
+            f_load_lower8(M + k0 * ld + k0, ld, Lk);
+            double acc0 = has ? qsm[u + tid] : 0.0, acc1 = 0.0;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) qsm[w + k0 + c] = y[c];
-            }
-            if (tid < k0) {
-                double acc = qsm[u + tid];
+            for (int c = 7; c >= 0; --c) {
+                y[c] *= Lk[QPB_LIDX(c, c)];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) acc = fma(-M[(k0 + c) * ld + tid], y[c], acc);
-                qsm[u + tid] = acc;
+                for (int c2 = 0; c2 < c; ++c2) y[c2] = fma(-y[c], Lk[QPB_LIDX(c, c2)], y[c2]);
+                if (has) { if (c & 1) acc1 = fma(-col[c], y[c], acc1); else acc0 = fma(-col[c], y[c], acc0); }
             }
+            if (tid == 0) f_st8(qsm + w + k0, y);
+            if (has) qsm[u + tid] = acc0 + acc1;
         }
         __syncthreads();
     }
@@ -348,10 +330,35 @@ __device__ __noinline__ void f_matvec_cols(int W, int ld, int rows, int cols, in
     __syncthreads();
 }
 
-// || L x ||^2 partial (packed lower L in shared memory)
+// || L x ||^2 partial sums (packed lower L in shared memory): 4 lanes per row, rows paired (r, n-1-r) for
+// balance, x cached in registers. Returns this thread's partial; sum over the block afterwards.
 __device__ __noinline__ double f_tri_norm2(int Lp, int n, int x) {
     QPB_SMEM;
-    return tri_norm2_partial(qsm + Lp, n, qsm + x, (int)threadIdx.x, kNT);
+    const int tid = threadIdx.x, q4 = tid >> 2, l = tid & 3;
+    constexpr int kMaxK = 32;                       // covers n <= 128; larger n falls back below
+    if (n > 4 * kMaxK) return tri_norm2_partial(qsm + Lp, n, qsm + x, tid, kNT);
+    double xr[kMaxK];
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) xr[k] = (l + 4 * k < n) ? qsm[x + l + 4 * k] : 0.0;
+    double acc = 0.0;
+    const int npairs = (n + 1) >> 1;
+    for (int pi = q4; pi < npairs + ((64 - npairs % 64) % 64); pi += 64) {   // warp-uniform trip count
+        const bool act = pi < npairs;
+        const int ra = act ? pi : 0, rb = n - 1 - ra;
+        const double* La = qsm + Lp + (ra * (ra + 1)) / 2;
+        const double* Lb = qsm + Lp + (rb * (rb + 1)) / 2;
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k) {
+            const int c = l + 4 * k;
+            if (act && c <= ra) sa = fma(La[c], xr[k], sa);
+            if (act && c <= rb && rb != ra) sb = fma(Lb[c], xr[k], sb);
+        }
+        sa += __shfl_xor_sync(0xffffffffu, sa, 1); sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+        sa += __shfl_xor_sync(0xffffffffu, sa, 2); sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+        if (l == 0) acc = fma(sa, sa, fma(sb, sb, acc));
+    }
+    return acc;
 }
 
 __device__ __noinline__ void f_reduce_sum4(double (&v)[4], int red) {

@@ -169,8 +169,8 @@ k_setup(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __restr
         if (c > r) RA[i] = 0.0;
     }
     __syncthreads();
-    // inverted diagonal blocks of the pre-factored equality columns ride along in the upper triangle
-    for (int blk = tid >> 5; blk < ep / 8; blk += nt >> 5) invert_diag8(RA, ldk, 8 * blk, 8, tid & 31);
+    // storage convention: the diagonal of the pre-factored equality columns holds 1 / L_cc
+    for (int i = tid; i < ep; i += nt) RA[i * ldk + i] = 1.0 / RA[i * ldk + i];
     __syncthreads();
     for (int i = tid; i < D.msp * D.lds; i += nt) {             // msp rows: identity-padded to a multiple of 8
         const int r = i / D.lds, c = i - r * D.lds;
@@ -322,7 +322,7 @@ __device__ __forceinline__ void unwhiten(const KDims& D, const Ctx& C, double* u
 // common prologue: reciprocal diagonals of L and of the pre-factored equality block
 __device__ __forceinline__ void load_dinvs(const KDims& D, const Ctx& C, int tid, int nt) {
     for (int i = tid; i < D.n; i += nt) VEC(V_DINVL)[i] = 1.0 / C.Lp[(i * (i + 1)) / 2 + i];
-    for (int i = tid; i < D.ep; i += nt) VEC(V_DINV)[i] = 1.0 / C.Kg[(int64_t)i * D.lds + i];
+    for (int i = tid; i < D.ep; i += nt) VEC(V_DINV)[i] = C.Kg[(int64_t)i * D.lds + i];   // K stores 1/L_cc there
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -748,7 +748,6 @@ __device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double*
     mbar_wait(bar, 0);
     // reciprocal diagonals of L (packed) and of the pre-factored equality block
     _Pragma("unroll 1") for (int i = tid; i < D.n; i += kNT) qsm[FV(F_DINVL) + i] = 1.0 / qsm[C.L.Lp + (i * (i + 1)) / 2 + i];
-    _Pragma("unroll 1") for (int i = tid; i < D.ep; i += kNT) qsm[FV(F_DINV) + i] = 1.0 / C.Kg[(int64_t)i * D.lds + i];
     return C;
 }
 
@@ -760,13 +759,13 @@ __device__ __forceinline__ void f_factor_and_solve(const KDims& D, FCtx& C) {
     _Pragma("unroll 1") for (int i = D.ep + tid; i < D.ms; i += kNT) qsm[C.L.LS + i * D.lds + i] += 1.0 / qsm[FV(F_D) + i];
     __syncthreads();
     if (D.ep > 0) {
-        f_trsv_fwd(C.L.LS, D.lds, D.msp, 0, D.ep, FV(F_DINV), FV(F_AUG), FV(F_T0));
+        f_trsv_fwd(C.L.LS, D.lds, D.msp, 0, D.ep, FV(F_AUG), FV(F_T0));
         _Pragma("unroll 1") for (int i = tid; i < D.ep; i += kNT) qsm[FV(F_AUG) + i] = qsm[FV(F_T0) + i];
         __syncthreads();
     }
-    f_chol(C.L.LS, D.lds, D.msp, D.ep, FV(F_AUG), FV(F_DINV), C.L.tab);
+    f_chol(C.L.LS, D.lds, D.msp, D.ep, FV(F_AUG), C.L.tab);
     QPB_TICK(32);   // (chol internals are 20..27)
-    f_trsv_bwd(C.L.LS, D.lds, D.msp, FV(F_DINV), FV(F_AUG), FV(F_W));
+    f_trsv_bwd(C.L.LS, D.lds, D.msp, FV(F_AUG), FV(F_W));
     QPB_TICK(33);   // backward substitution
 }
 
@@ -787,7 +786,8 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     const int qp = blockIdx.x;
     const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
 #ifdef QPB_TIMING
-    if (threadIdx.x == 0 && blockIdx.x == 0) g_tlast = clock64();
+    if (threadIdx.x == 0) { for (int i = 0; i < 64; ++i) s_tim[i] = 0; s_tim[64] = clock64(); }
+    __syncthreads();
 #endif
     FCtx C = f_make_ctx(D, qp, Lfac, Wfac, Kfac, sF);
     QPB_TICK(0);
@@ -930,9 +930,9 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
             __syncthreads();
         }
         QPB_TICK(11);
-        f_trsv_fwd(C.L.LS, D.lds, msp, 0, msp, FV(F_DINV), t1, t0);
+        f_trsv_fwd(C.L.LS, D.lds, msp, 0, msp, t1, t0);
         QPB_TICK(12);
-        f_trsv_bwd(C.L.LS, D.lds, msp, FV(F_DINV), t0, t1);      // t1 = [dy_cor; dz_cor]
+        f_trsv_bwd(C.L.LS, D.lds, msp, t0, t1);                  // t1 = [dy_cor; dz_cor]
         QPB_TICK(13);
         f_issue_K(D, C);                                         // next factor_kkt's K copy overlaps the rest
         // ---- combined direction, step length, update (batch.py:185-203)
@@ -981,6 +981,9 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         iters_out[qp] = iters_run;
         resid_out[qp] = ret_resid;
     }
+#ifdef QPB_TIMING
+    if (tid == 0 && qp == 0) for (int i = 0; i < 64; ++i) g_tim[i] = s_tim[i];
+#endif
 }
 
 template <bool kBackward>
