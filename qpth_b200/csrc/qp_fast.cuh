@@ -31,8 +31,19 @@ __shared__ long long s_tim[65];
             s_tim[64] = _t;                                                 \
         }                                                                   \
     } while (0)
+// second clock on thread 32 (warp 1, an update warp): slots 40.., own time base in s_tim2
+__shared__ long long s_tim2;
+#define QPB_TICK1(i)                                                        \
+    do {                                                                    \
+        if (threadIdx.x == 32) {                                            \
+            const long long _t = clock64();                                 \
+            s_tim[i] += _t - s_tim2;                                        \
+            s_tim2 = _t;                                                    \
+        }                                                                   \
+    } while (0)
 #else
 #define QPB_TICK(i) do {} while (0)
+#define QPB_TICK1(i) do {} while (0)
 #endif
 
 constexpr int kNT = 256;
@@ -53,6 +64,43 @@ __device__ __forceinline__ void f_load_lower8(const double* Mb, int ld, double (
         }
 }
 
+// 1/sqrt(x) for the pivots: MUFU seed (~23 bits) + one third-order step; 4 dependent fp64 ops after the MUFU
+// instead of the library rsqrt()'s 5 + special-case branch (measured on B200: 8x8 factor 556 vs 716 cycles).
+// Negative / zero pivots give NaN, which is what the callers want to propagate.
+__device__ __forceinline__ double f_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double ye = y * e;
+    return fma(ye, p, y);
+}
+
+// In-register factorization of an 8x8 block (lower triangle in Lk): on exit strictly lower = L, diagonal = 1/L_cc.
+__device__ __forceinline__ void f_factor8_regs(double (&Lk)[36]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double ri = f_rsqrt(Lk[QPB_LIDX(c, c)]);
+        Lk[QPB_LIDX(c, c)] = ri;
+#pragma unroll
+        for (int r = c + 1; r < 8; ++r) Lk[QPB_LIDX(r, c)] *= ri;
+#pragma unroll
+        for (int r = c + 1; r < 8; ++r)
+#pragma unroll
+            for (int cc = c + 1; cc <= r; ++cc)
+                Lk[QPB_LIDX(r, cc)] = fma(-Lk[QPB_LIDX(r, c)], Lk[QPB_LIDX(cc, c)], Lk[QPB_LIDX(r, cc)]);
+    }
+}
+__device__ __forceinline__ void f_store_lower8(double* Mb, int ld, const double (&Lk)[36]) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; c += 2)      // the odd tail writes one element of the (unused) upper part
+            *reinterpret_cast<double2*>(Mb + r * ld + c) =
+                make_double2(Lk[QPB_LIDX(r, c)], (c + 1 <= r) ? Lk[QPB_LIDX(r, c + 1)] : 0.0);
+}
+
 // Factor the 8x8 block at Mb redundantly in every lane of the calling warp; lane 0 writes it back
 // (strictly lower = L, diagonal = rsqrt(pivot)).
 __device__ __noinline__ void f_factor8(int Mb_off, int ld) {
@@ -60,6 +108,7 @@ __device__ __noinline__ void f_factor8(int Mb_off, int ld) {
     double* Mb = qsm + Mb_off;
     double Lk[36];
     f_load_lower8(Mb, ld, Lk);
+    __syncwarp();
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const double ri = rsqrt(Lk[QPB_LIDX(c, c)]);
@@ -105,58 +154,55 @@ __device__ __forceinline__ void f_st8(double* p, const double (&a)[8]) {
     *reinterpret_cast<double2*>(p + 6) = make_double2(a[6], a[7]);
 }
 
-// ---- Cholesky: register-resident off-diagonal tiles (warps 1..7), look-ahead on warp 0 ------------------
+// ---- Cholesky: register-resident off-diagonal tiles, warp 0 runs the critical chain one panel ahead -----
 // n multiple of 8, (n - c0)/8 <= 13, blockDim.x == 256. aug (offset) = right-hand side (length n) carried
 // along so that L^-1 aug falls out of the factorization. Diagonal blocks end up in the convention above.
-__device__ __noinline__ void f_chol(int A, int ld, int n, int c0, int aug, int tabo) {
+//
+// Tasks of panel k:  F_k  factor diagonal block k                         (needs tile (k,k) final)
+//                    s_k  solve the 8 panel rows of block k+1             (needs F_k)
+//                    u_k  update diagonal tile k+1 with those rows        (needs s_k)      } critical chain,
+//                    S_k  solve all other panel rows + the aug row        (needs F_k)        all on warp 0
+//                    U_k  rest of the trailing update with panel k        (needs s_k, S_k)
+// One step = [warp 0: s_k, u_k, F_{k+1}] in parallel with [warps 1..7: S_k, then U_k]; warp 0 signals s_k through
+// named barrier 1 (bar.arrive, never waits), one __syncthreads per step. Warp 4 shares its scheduler with warp 0
+// and takes no DMMA work, so the rsqrt/DFMA chain of F runs uncontended.
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// Role 1 (warp 0): the critical chain  F_0, then per step  s_k -> signal -> u_k -> F_{k+1}.
+__device__ __noinline__ void f_chol_chain(int A, int ld, int n, int c0) {
     QPB_SMEM;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     const int nts = (n - c0) >> 3;
-    const int noff = (nts * (nts - 1)) / 2;
-    const uint16_t* tab = reinterpret_cast<const uint16_t*>(qsm + tabo);
     double* M = qsm + A;
-    // update warps: 1,2,3,5,6,7 -> uw = 0..5. Warp 4 shares its scheduler (and fp64 pipe) with the critical
-    // warp 0, so it takes no DMMA work: the factor chain on warp 0 then runs uncontended.
-    const int uw = (warp == 0 || warp == 4) ? -1 : (warp < 4 ? warp - 1 : warp - 2);
-    double C[kCholMaxOff][2];
-    if (warp == 0) {
-        f_factor8(A + c0 * ld + c0, ld);
-    } else if (uw >= 0) {
-#pragma unroll
-        for (int s = 0; s < kCholMaxOff; ++s) {
-            const int idx = s * 6 + uw;
-            const bool ok = idx < noff;
-            const int tt = ok ? tab[idx] : 0;
-            const double2 v = ok ? *reinterpret_cast<const double2*>(M + (c0 + 8 * (tt >> 8) + g) * ld + c0 + 8 * (tt & 255) + 2 * q)
-                                 : make_double2(0.0, 0.0);
-            C[s][0] = v.x; C[s][1] = v.y;
-        }
-    }
+    double Lk[36];                                           // the current diagonal block stays in registers
+    f_load_lower8(M + c0 * ld + c0, ld, Lk);
+    __syncwarp();
+    f_factor8_regs(Lk);                                                               // F_0
+    if (lane == 0) f_store_lower8(M + c0 * ld + c0, ld, Lk);
     QPB_TICK(20);
     __syncthreads();
     QPB_TICK(21);
     for (int k = 0; k < nts; ++k) {
         const int k0 = c0 + 8 * k;
-        // ---- phase A: rows below the diagonal block (and the aug row): row <- row * L_kk^-T
-        {
-            const int nbelow = n - k0 - 8;
-            if (tid <= nbelow) {
-                double Lk[36], a[8];
-                double* rowp = (tid < nbelow) ? (M + (k0 + 8 + tid) * ld + k0) : (qsm + aug + k0);
+        if (k + 1 < nts) {
+            // ---- s_k: the 8 panel rows of block k+1 (lanes 0..7), L_kk still in registers from F_k
+            if (lane < 8) {
+                double a[8];
+                double* rowp = M + (k0 + 8 + lane) * ld + k0;
                 f_ld8(rowp, a);
-                f_load_lower8(M + k0 * ld + k0, ld, Lk);
                 f_row_solve8(a, Lk);
                 f_st8(rowp, a);
             }
-        }
-        QPB_TICK(22);
-        __syncthreads();
-        QPB_TICK(23);
-        if (k + 1 >= nts) break;
-        // ---- phase B: trailing update with panel k
-        if (warp == 0) {
-            // look-ahead: bring diagonal tile k+1 up to date (it lives in shared memory) and factor it
+            __syncwarp();
+            named_bar_arrive(1, kNT);
+            QPB_TICK(22);
+            // ---- u_k: diagonal tile k+1 (lives in shared memory)
             double* pd = M + (k0 + 8 + g) * ld + k0 + 8 + 2 * q;
             const double* pr = M + (k0 + 8 + g) * ld + k0 + q;
             double2 cv = *reinterpret_cast<const double2*>(pd);
@@ -166,38 +212,104 @@ __device__ __noinline__ void f_chol(int A, int ld, int n, int c0, int aug, int t
             *reinterpret_cast<double2*>(pd) = cv;
             __syncwarp();
             QPB_TICK(24);
-            f_factor8(A + (k0 + 8) * ld + k0 + 8, ld);
+            f_load_lower8(M + (k0 + 8) * ld + k0 + 8, ld, Lk);
+            __syncwarp();                                                             // all lanes have read the tile
+            f_factor8_regs(Lk);                                                       // F_{k+1}
+            if (lane == 0) f_store_lower8(M + (k0 + 8) * ld + k0 + 8, ld, Lk);
             QPB_TICK(25);
-        } else if (uw >= 0) {
+        }
+        QPB_TICK(26);
+        __syncthreads();
+        QPB_TICK(27);
+    }
+}
+
+// Role 2 (warps 1..7): per step  S_k (all other panel rows + the aug row), wait for s_k, then U_k.
+// Update warps 1,2,3,5,6,7 own the off-diagonal tiles as DMMA accumulators in registers; warp 4 shares its
+// scheduler (and fp64 pipe) with the chain warp, so it only carries the right-hand side along.
+__device__ __noinline__ void f_chol_update(int A, int ld, int n, int c0, int aug, int tabo) {
+    QPB_SMEM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int nts = (n - c0) >> 3;
+    const int noff = (nts * (nts - 1)) / 2;
+    const uint16_t* tab = reinterpret_cast<const uint16_t*>(qsm + tabo);
+    double* M = qsm + A;
+    const int uw = (warp == 4) ? -1 : (warp < 4 ? warp - 1 : warp - 2);
+    double C[kCholMaxOff][2];
+    int tj_of[kCholMaxOff];                                  // column block of each owned tile (-1: empty slot)
+    int offA[kCholMaxOff], offB[kCholMaxOff];                // fragment base offsets (rows of block ti / tj)
+    if (uw >= 0) {
 #pragma unroll
-            for (int s = 0; s < kCholMaxOff; ++s) {
-                const int idx = s * 6 + uw;
-                if (idx < noff) {
-                    const int tt = tab[idx];
-                    const int ti = tt >> 8, tj = tt & 255;
-                    if (tj > k) {
-                        const double* pa = M + (c0 + 8 * ti + g) * ld + k0 + q;
-                        const double* pb = M + (c0 + 8 * tj + g) * ld + k0 + q;
-                        const double a0 = pa[0], a1 = pa[4], b0 = pb[0], b1 = pb[4];
-                        dmma884(C[s][0], C[s][1], -a0, b0);
-                        dmma884(C[s][0], C[s][1], -a1, b1);
-                        if (tj == k + 1)       // this tile belongs to the next panel: publish it
-                            *reinterpret_cast<double2*>(M + (c0 + 8 * ti + g) * ld + c0 + 8 * tj + 2 * q) =
-                                make_double2(C[s][0], C[s][1]);
-                    }
+        for (int s = 0; s < kCholMaxOff; ++s) {
+            const int idx = s * 6 + uw;
+            const bool ok = idx < noff;
+            const int tt = ok ? tab[idx] : 0;
+            tj_of[s] = ok ? (tt & 255) : -1;
+            offA[s] = (c0 + 8 * (tt >> 8) + g) * ld + q;
+            offB[s] = (c0 + 8 * (tt & 255) + g) * ld + q;
+            const double2 v = ok ? *reinterpret_cast<const double2*>(M + (c0 + 8 * (tt >> 8) + g) * ld + c0 + 8 * (tt & 255) + 2 * q)
+                                 : make_double2(0.0, 0.0);
+            C[s][0] = v.x; C[s][1] = v.y;
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < nts; ++k) {
+        const int k0 = c0 + 8 * k;
+        const bool last = (k + 1 >= nts);
+        QPB_TICK1(40);
+        // ---- S_k: all other rows below (i >= k0 + 16) and the aug row: row <- row * L_kk^-T
+        {
+            const int t = tid - 32;
+            const int nrows = n - k0 - 16;                  // may be <= 0 near the end
+            const int naug = nrows > 0 ? nrows : 0;
+            if (t <= naug) {
+                double Ls[36], a[8];
+                double* rowp = (t < naug) ? (M + (k0 + 16 + t) * ld + k0) : (qsm + aug + k0);
+                f_ld8(rowp, a);
+                f_load_lower8(M + k0 * ld + k0, ld, Ls);
+                f_row_solve8(a, Ls);
+                f_st8(rowp, a);
+            }
+        }
+        QPB_TICK1(41);
+        if (!last) {
+            named_bar_sync(1, kNT);                         // all panel rows (incl. the chain warp's) are in place
+            QPB_TICK1(42);
+            if (uw >= 0) {
+                // tiles come column by column, so the active ones (tj > k) are a suffix of this warp's slots;
+                // two tiles at a time: 4 independent DMMAs keep the pipe busy
+#pragma unroll
+                for (int s = kCholMaxOff - 1; s >= 0; s -= 2) {
+                    const int s1 = s, s2 = (s - 1 >= 0) ? s - 1 : 0;
+                    const bool act1 = tj_of[s1] > k;                           // warp-uniform
+                    const bool act2 = (s - 1 >= 0) && (tj_of[s2] > k);
+                    if (!act1 && !act2) continue;
+                    double a10 = 0, a11 = 0, b10 = 0, b11 = 0, a20 = 0, a21 = 0, b20 = 0, b21 = 0;
+                    if (act1) { const double* pa = M + offA[s1] + k0; const double* pb = M + offB[s1] + k0;
+                                a10 = pa[0]; a11 = pa[4]; b10 = pb[0]; b11 = pb[4]; }
+                    if (act2) { const double* pa = M + offA[s2] + k0; const double* pb = M + offB[s2] + k0;
+                                a20 = pa[0]; a21 = pa[4]; b20 = pb[0]; b21 = pb[4]; }
+                    if (act1) dmma884(C[s1][0], C[s1][1], -a10, b10);
+                    if (act2) dmma884(C[s2][0], C[s2][1], -a20, b20);
+                    if (act1) dmma884(C[s1][0], C[s1][1], -a11, b11);
+                    if (act2) dmma884(C[s2][0], C[s2][1], -a21, b21);
+                    if (act1 && tj_of[s1] == k + 1)            // this tile belongs to the next panel: publish it
+                        *reinterpret_cast<double2*>(M + offA[s1] + q + c0 + 8 * (k + 1)) = make_double2(C[s1][0], C[s1][1]);
+                    if (act2 && tj_of[s2] == k + 1)
+                        *reinterpret_cast<double2*>(M + offA[s2] + q + c0 + 8 * (k + 1)) = make_double2(C[s2][0], C[s2][1]);
                 }
-            }
-            // remaining diagonal tiles (s > k+1) are updated in place in shared memory, spread over warps 1..7
-            for (int s = k + 2 + uw; s < nts; s += 6) {
-                double* pd = M + (c0 + 8 * s + g) * ld + c0 + 8 * s + 2 * q;
-                const double* pr = M + (c0 + 8 * s + g) * ld + k0 + q;
-                double2 cv = *reinterpret_cast<const double2*>(pd);
-                const double a0 = pr[0], a1 = pr[4];
-                dmma884(cv.x, cv.y, -a0, a0);
-                dmma884(cv.x, cv.y, -a1, a1);
-                *reinterpret_cast<double2*>(pd) = cv;
-            }
-            if (warp == 7) {                    // right-hand side: aug[j] -= P[j][:] . y
+                // diagonal tiles s > k+1 are updated in place in shared memory, spread over the update warps
+                for (int s = k + 2 + uw; s < nts; s += 6) {
+                    double* pd = M + (c0 + 8 * s + g) * ld + c0 + 8 * s + 2 * q;
+                    const double* pr = M + (c0 + 8 * s + g) * ld + k0 + q;
+                    double2 cv = *reinterpret_cast<const double2*>(pd);
+                    const double a0 = pr[0], a1 = pr[4];
+                    dmma884(cv.x, cv.y, -a0, a0);
+                    dmma884(cv.x, cv.y, -a1, a1);
+                    *reinterpret_cast<double2*>(pd) = cv;
+                }
+            } else {                                        // warp 4: right-hand side, aug[j] -= P[j][:] . y
                 double y[8];
                 f_ld8(qsm + aug + k0, y);
                 for (int j = k0 + 8 + lane; j < n; j += 32) {
@@ -210,10 +322,17 @@ __device__ __noinline__ void f_chol(int A, int ld, int n, int c0, int aug, int t
                 }
             }
         }
-        QPB_TICK(26);
+        QPB_TICK1(43);
         __syncthreads();
-        QPB_TICK(27);
+        QPB_TICK1(44);
     }
+}
+
+// n multiple of 8, (n - c0)/8 <= 13, blockDim.x == 256. aug (offset) = right-hand side (length n) carried along so
+// that L^-1 aug falls out of the factorization. Two roles with separate register allocations.
+__device__ __forceinline__ void f_chol(int A, int ld, int n, int c0, int aug, int tabo) {
+    if (threadIdx.x < 32) f_chol_chain(A, ld, n, c0);
+    else f_chol_update(A, ld, n, c0, aug, tabo);
 }
 
 // ---- triangular solves by substitution on 8-blocks (n multiple of 8) --------------------------------------

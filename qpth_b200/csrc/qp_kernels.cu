@@ -786,7 +786,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     const int qp = blockIdx.x;
     const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
 #ifdef QPB_TIMING
-    if (threadIdx.x == 0) { for (int i = 0; i < 64; ++i) s_tim[i] = 0; s_tim[64] = clock64(); }
+    if (threadIdx.x == 0) { for (int i = 0; i < 64; ++i) s_tim[i] = 0; s_tim[64] = clock64(); s_tim2 = s_tim[64]; }
     __syncthreads();
 #endif
     FCtx C = f_make_ctx(D, qp, Lfac, Wfac, Kfac, sF);

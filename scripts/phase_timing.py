@@ -19,11 +19,11 @@ lib.qpb200_debug_timing(None, 1)
 f(t["Q"], t["p"], t["G"], t["h"], t["A"], t["b"]); torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 64)()
 lib.qpb200_debug_timing(buf, 0)
-it = int(f.last_solve().iters[0])
+torch.cuda.synchronize(); it = int(f.last_solve().iters.cpu()[0]); print('iters', f.last_solve().iters.cpu()[:8].tolist(), 'resid', f.last_solve().best_resid.cpu()[:3].tolist())
 names = {0: "make_ctx (TMA W,L)", 1: "load vectors", 2: "whiten", 3: "loop misc/update (prev)", 4: "matvec_cols (r~x)", 5: "matvec_rows2", 6: "residual elementwise", 7: "tri_norm2", 8: "reduce_sum4",
          9: "best/exit/aug build", 10: "factor_and_solve tail", 11: "aff step, sigma, rhs", 12: "trsv_fwd (cor)", 13: "trsv_bwd (cor)", 14: "issue_K + combine", 15: "matvec_cols (dx)", 16: "final misc",
          20: "chol: tile load + first factor", 21: "chol: first barrier", 22: "chol: phase A work", 23: "chol: barrier after A", 24: "chol: diag tile k+1 update", 25: "chol: factor8", 26: "chol: (other warps) / end B", 27: "chol: barrier after B",
-         30: "wait K copy", 31: "diag add + barrier", 32: "chol exit", 33: "trsv_bwd (aff)"}
+         40: "[warp1] gap", 41: "[warp1] S_k rows", 42: "[warp1] named barrier wait", 43: "[warp1] U_k update", 44: "[warp1] step barrier wait", 30: "wait K copy", 31: "diag add + barrier", 32: "chol exit", 33: "trsv_bwd (aff)"}
 tot = sum(buf)
 print("QP 0 of block 0: %d iterations; total %d cycles (%.1f us @1.965GHz); per iteration %.0f" % (it, tot, tot / 1965.0, tot / (it + 1)))
 for i in range(64):
