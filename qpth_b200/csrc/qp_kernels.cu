@@ -1131,9 +1131,26 @@ KDims dims_of(const qpb200_plan* p) {
     return D;
 }
 
+// cudaFuncSetAttribute is not free (and may serialise with the driver): raise the dynamic shared-memory
+// limit of a kernel only when it has to grow. Keyed by (device, kernel).
+struct SmemSet { const void* fn; int dev; size_t bytes; };
+SmemSet g_smem_set[64];
+int g_smem_n = 0;
+
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    for (int i = 0; i < g_smem_n; ++i)
+        if (g_smem_set[i].fn == fn && g_smem_set[i].dev == dev) {
+            if (g_smem_set[i].bytes >= bytes) return QPB200_OK;
+            CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            g_smem_set[i].bytes = bytes;
+            return QPB200_OK;
+        }
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (g_smem_n < 64) g_smem_set[g_smem_n++] = SmemSet{fn, dev, bytes};
     return QPB200_OK;
 }
 
