@@ -49,6 +49,7 @@ typedef struct qpb200_plan {
     int smem_resident;      /* 1: W and the S workspace live in shared memory; 0: global scratch */
     int threads;            /* CTA size the kernels are launched with */
     int fast;               /* 1: compact shared-memory kernels (register-resident Cholesky, nineq <= 104) */
+    int setup_fast;         /* 1: pre_factor_kkt with the same building blocks (nz <= 104) */
     int64_t L_elems;        /* per system: chol(Q), packed lower triangle, row by row    [replaces Q_LU]  */
     int64_t W_elems;        /* per system: [A;G] L^-T, ms rows with stride ldw           [whitened G, A]  */
     int64_t K_elems;        /* per system: block-Cholesky template of S, ms_pad x lds    [replaces S_LU,R] */

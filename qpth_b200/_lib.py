@@ -19,7 +19,7 @@ class Plan(ctypes.Structure):
         ("nz", ctypes.c_int), ("nineq", ctypes.c_int), ("neq", ctypes.c_int),
         ("neq_pad", ctypes.c_int), ("ms", ctypes.c_int), ("ms_pad", ctypes.c_int),
         ("ldw", ctypes.c_int), ("lds", ctypes.c_int), ("rows_s", ctypes.c_int), ("vl", ctypes.c_int),
-        ("smem_resident", ctypes.c_int), ("threads", ctypes.c_int), ("fast", ctypes.c_int),
+        ("smem_resident", ctypes.c_int), ("threads", ctypes.c_int), ("fast", ctypes.c_int), ("setup_fast", ctypes.c_int),
         ("L_elems", ctypes.c_int64), ("W_elems", ctypes.c_int64), ("K_elems", ctypes.c_int64),
         ("setup_scratch_elems", ctypes.c_int64), ("solve_scratch_elems", ctypes.c_int64),
         ("setup_smem_bytes", ctypes.c_int64), ("solve_smem_bytes", ctypes.c_int64),

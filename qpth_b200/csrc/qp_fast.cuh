@@ -20,15 +20,15 @@ namespace fast {
 // Optional cycle accounting (build with -DQPB_TIMING): thread 0 of block 0 accumulates clock64() deltas per
 // phase into g_tim[]; read back with qpb200_debug_timing(). Compiled out of the product build.
 #ifdef QPB_TIMING
-__device__ long long g_tim[64];
+__device__ long long g_tim[128];
 // accumulators live in (static) shared memory so that a tick costs ~40 cycles, not a global round trip
-__shared__ long long s_tim[65];
+__shared__ long long s_tim[129];
 #define QPB_TICK(i)                                                         \
     do {                                                                    \
         if (threadIdx.x == 0) {                                             \
             const long long _t = clock64();                                 \
-            s_tim[i] += _t - s_tim[64];                                     \
-            s_tim[64] = _t;                                                 \
+            s_tim[i] += _t - s_tim[128];                                    \
+            s_tim[128] = _t;                                                \
         }                                                                   \
     } while (0)
 // second clock on thread 32 (warp 1, an update warp): slots 40.., own time base in s_tim2
@@ -201,7 +201,7 @@ __device__ __noinline__ void f_chol_chain(int A, int ld, int n, int c0) {
             }
             __syncwarp();
             named_bar_arrive(1, kNT);
-            QPB_TICK(22);
+            QPB_TICK(96 + k);   // s_k, per step
             // ---- u_k: diagonal tile k+1 (lives in shared memory)
             double* pd = M + (k0 + 8 + g) * ld + k0 + 8 + 2 * q;
             const double* pr = M + (k0 + 8 + g) * ld + k0 + q;
@@ -216,11 +216,11 @@ __device__ __noinline__ void f_chol_chain(int A, int ld, int n, int c0) {
             __syncwarp();                                                             // all lanes have read the tile
             f_factor8_regs(Lk);                                                       // F_{k+1}
             if (lane == 0) f_store_lower8(M + (k0 + 8) * ld + k0 + 8, ld, Lk);
-            QPB_TICK(25);
+            QPB_TICK(80 + k);   // F_{k+1}, per step
         }
         QPB_TICK(26);
         __syncthreads();
-        QPB_TICK(27);
+        QPB_TICK(112 + k);      // chain warp waiting for the update warps, per step
     }
 }
 
@@ -272,7 +272,7 @@ __device__ __noinline__ void f_chol_update(int A, int ld, int n, int c0, int aug
                 f_st8(rowp, a);
             }
         }
-        QPB_TICK1(41);
+        QPB_TICK1(64 + k);      // S_k, per step
         if (!last) {
             named_bar_sync(1, kNT);                         // all panel rows (incl. the chain warp's) are in place
             QPB_TICK1(42);
@@ -322,7 +322,7 @@ __device__ __noinline__ void f_chol_update(int A, int ld, int n, int c0, int aug
                 }
             }
         }
-        QPB_TICK1(43);
+        QPB_TICK1(48 + k);      // U_k, per step
         __syncthreads();
         QPB_TICK1(44);
     }
@@ -395,6 +395,69 @@ __device__ __noinline__ void f_trsv_bwd(int A, int ld, int n, int u, int w) {
     }
 }
 
+// Invert a factored 8x8 diagonal block (strictly lower = L, diagonal = 1/L_cc): T = L_kk^-1. T's strictly
+// lower part is written TRANSPOSED into the (unused) upper triangle of the block; its diagonal is the
+// reciprocal diagonal already there. One lane does the work (pre_factor_kkt only; off the Newton loop).
+__device__ __noinline__ void f_invert8(int Mb_off, int ld) {
+    QPB_SMEM;
+    double* Mb = qsm + Mb_off;
+    if ((threadIdx.x & 31) == 0) {
+        double Lk[36], T[36];
+        f_load_lower8(Mb, ld, Lk);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            T[QPB_LIDX(c, c)] = Lk[QPB_LIDX(c, c)];
+#pragma unroll
+            for (int r = c + 1; r < 8; ++r) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int j = c; j < r; ++j) sacc = fma(Lk[QPB_LIDX(r, j)], T[QPB_LIDX(j, c)], sacc);
+                T[QPB_LIDX(r, c)] = -Lk[QPB_LIDX(r, r)] * sacc;
+            }
+        }
+#pragma unroll
+        for (int r = 1; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < r; ++c) Mb[c * ld + r] = T[QPB_LIDX(r, c)];
+    }
+    __syncwarp();
+}
+
+// W row tile `rt` (8 rows) <- rows * L^-T for the factored n x n matrix at A (n multiple of 8, diagonal blocks
+// in the reciprocal-diagonal convention with T^T in their upper triangles). Left-looking over column tiles,
+// all inside ONE warp: no block-level synchronisation, row tiles are independent of each other.
+__device__ __noinline__ void f_rows_times_LinvT(int A, int ld, int n, int Wm, int ldw, int rt) {
+    QPB_SMEM;
+    const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const double* M = qsm + A;
+    double* Wp = qsm + Wm + (8 * rt + g) * ldw;              // this lane's row of the tile
+    const int nct = n >> 3;
+    for (int j = 0; j < nct; ++j) {
+        double2 cv = *reinterpret_cast<const double2*>(Wp + 8 * j + 2 * q);
+        const double* pb = M + (8 * j + g) * ld + q;         // rows of block j of L, panel columns follow
+        for (int i = 0; i < j; ++i) {
+            const double a0 = Wp[8 * i + q], a1 = Wp[8 * i + 4 + q];
+            const double b0 = pb[8 * i], b1 = pb[8 * i + 4];
+            dmma884(cv.x, cv.y, -a0, b0);
+            dmma884(cv.x, cv.y, -a1, b1);
+        }
+        *reinterpret_cast<double2*>(Wp + 8 * j + 2 * q) = cv;
+        __syncwarp();
+        // tile <- tile * T_jj^T   (B[k][nn] = T[nn][k]; T lower: reciprocal diagonal, strictly lower part stored transposed)
+        const double a0 = Wp[8 * j + q], a1 = Wp[8 * j + 4 + q];
+        const double* Tb = M + (8 * j) * ld + 8 * j;
+        const int c0 = q, c1 = 4 + q;
+        const double b0 = (c0 < g) ? Tb[c0 * ld + g] : (c0 == g ? Tb[g * ld + g] : 0.0);
+        const double b1 = (c1 < g) ? Tb[c1 * ld + g] : (c1 == g ? Tb[g * ld + g] : 0.0);
+        double d0 = 0.0, d1 = 0.0;
+        dmma884(d0, d1, a0, b0);
+        dmma884(d0, d1, a1, b1);
+        __syncwarp();
+        *reinterpret_cast<double2*>(Wp + 8 * j + 2 * q) = make_double2(d0, d1);
+        __syncwarp();
+    }
+}
+
 // ---- packed-L substitution (x~ = L^-1 x, x = L^-T x~): twice per kernel, off the hot loop ----------------
 __device__ __noinline__ void f_whiten(int Lp, int n, int dinvL, int b, int u) {
     QPB_SMEM;
@@ -406,14 +469,54 @@ __device__ __noinline__ void f_unwhiten(int Lp, int n, int dinvL, int u, int w) 
 }
 
 // ---- mat-vecs with W (rows x cols, ld) ---------------------------------------------------------------------
-// y1 = W x1, y2 = W x2 (4 lanes per row, conflict free for ld % 8 == 4)
-__device__ __noinline__ void f_matvec_rows2(int W, int ld, int rows, int cols, int x1, int x2, int y1, int y2) {
+// y1 = W x1, y2 = W x2 (4 lanes per row, conflict free for ld % 8 == 4). The slices of x1/x2 a lane needs are
+// cached in registers, so the loop streams W only (one LDS per two FMAs instead of three).
+template <bool kTwo>
+__device__ __forceinline__ void f_matvec_rows_impl(int W, int ld, int rows, int cols, int x1, int x2, int y1, int y2) {
     QPB_SMEM;
-    matvec_rows<true>(qsm + W, ld, rows, cols, qsm + x1, qsm + x2, qsm + y1, qsm + y2, (int)threadIdx.x, kNT);
+    const int tid = threadIdx.x, q4 = tid >> 2, l = tid & 3;
+    constexpr int kMaxK = 26;                                // cols <= 104
+    if (cols > 4 * kMaxK) {
+        matvec_rows<kTwo>(qsm + W, ld, rows, cols, qsm + x1, kTwo ? qsm + x2 : nullptr, qsm + y1, kTwo ? qsm + y2 : nullptr, tid, kNT);
+        return;
+    }
+    double xa[kMaxK], xb[kMaxK];
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) {
+        const int c = l + 4 * k;
+        xa[k] = (c < cols) ? qsm[x1 + c] : 0.0;
+        xb[k] = (kTwo && c < cols) ? qsm[x2 + c] : 0.0;
+    }
+    for (int rb = 0; rb < rows; rb += kNT / 4) {
+        const int r = rb + q4;
+        const bool ok = r < rows;
+        const double* a = qsm + W + (ok ? r : 0) * ld + l;
+        double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
+#pragma unroll
+        for (int k = 0; k < kMaxK; k += 2) {
+            const double w0 = (ok && l + 4 * k < cols) ? a[4 * k] : 0.0;
+            const double w1 = (ok && l + 4 * k + 4 < cols) ? a[4 * k + 4] : 0.0;
+            s1a = fma(w0, xa[k], s1a); s1b = fma(w1, xa[k + 1], s1b);
+            if (kTwo) { s2a = fma(w0, xb[k], s2a); s2b = fma(w1, xb[k + 1], s2b); }
+        }
+        double s1 = s1a + s1b, s2 = s2a + s2b;
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        if (kTwo) {
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+        }
+        if (ok && l == 0) {
+            qsm[y1 + r] = s1;
+            if (kTwo) qsm[y2 + r] = s2;
+        }
+    }
+}
+__device__ __noinline__ void f_matvec_rows2(int W, int ld, int rows, int cols, int x1, int x2, int y1, int y2) {
+    f_matvec_rows_impl<true>(W, ld, rows, cols, x1, x2, y1, y2);
 }
 __device__ __noinline__ void f_matvec_rows1(int W, int ld, int rows, int cols, int x1, int y1) {
-    QPB_SMEM;
-    matvec_rows<false>(qsm + W, ld, rows, cols, qsm + x1, nullptr, qsm + y1, nullptr, (int)threadIdx.x, kNT);
+    f_matvec_rows_impl<false>(W, ld, rows, cols, x1, 0, y1, 0);
 }
 // out[c] = a[c] + sgn * (W^T v)[c] (+ b[c] if b >= 0). Two row groups, partial sums in p0/p1.
 __device__ __noinline__ void f_matvec_cols(int W, int ld, int rows, int cols, int v, int p0, int p1, int out,

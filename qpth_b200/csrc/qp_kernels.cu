@@ -786,7 +786,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     const int qp = blockIdx.x;
     const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
 #ifdef QPB_TIMING
-    if (threadIdx.x == 0) { for (int i = 0; i < 64; ++i) s_tim[i] = 0; s_tim[64] = clock64(); s_tim2 = s_tim[64]; }
+    if (threadIdx.x == 0) { for (int i = 0; i < 128; ++i) s_tim[i] = 0; s_tim[128] = clock64(); s_tim2 = s_tim[128]; }
     __syncthreads();
 #endif
     FCtx C = f_make_ctx(D, qp, Lfac, Wfac, Kfac, sF);
@@ -982,7 +982,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         resid_out[qp] = ret_resid;
     }
 #ifdef QPB_TIMING
-    if (tid == 0 && qp == 0) for (int i = 0; i < 64; ++i) g_tim[i] = s_tim[i];
+    if (tid == 0 && qp == 0) for (int i = 0; i < 128; ++i) g_tim[i] = s_tim[i];
 #endif
 }
 
@@ -1096,6 +1096,168 @@ k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_setup_fast: pre_factor_kkt (batch.py:375-429) with the fast building blocks.
+//   1. chol(Q) with the pipelined f_chol (Q identity-padded to a multiple of 8),
+//   2. T = L_kk^-1 for every diagonal block (warps in parallel),
+//   3. W = [A; 0; G] L^-T: every 8-row tile independently inside one warp (left-looking, DMMA), no barriers,
+//   4. K = W W^T (DMMA), unit diagonal on dummy / pad rows, partial Cholesky of the equality columns.
+// ---------------------------------------------------------------------------------------------
+namespace fk {
+struct SLayout { int QA, WA, aug, tab, np, ldq, total; };
+__host__ __device__ inline SLayout setup_layout(const KDims& D) {
+    SLayout L;
+    L.np = (D.n + 7) & ~7;
+    L.ldq = ld_for(L.np);
+    const int qa = L.np * L.ldq, ka = D.msp * D.lds;
+    L.QA = 0;
+    L.WA = qa > ka ? qa : ka;
+    L.aug = L.WA + D.msp * L.ldq;
+    L.tab = L.aug + (((L.np > D.msp ? L.np : D.msp) + 7) & ~7);
+    L.total = L.tab + kTabDoubles;
+    return L;
+}
+}  // namespace fk
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_setup_fast(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __restrict__ G, int64_t sG,
+             const double* __restrict__ A, int64_t sA, double* __restrict__ Lfac, double* __restrict__ Wfac,
+             double* __restrict__ Kfac, int* __restrict__ spd_flag) {
+    using namespace fk;
+    QPB_SMEM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sys = blockIdx.x;
+    const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
+    const SLayout S = setup_layout(D);
+    const int np = S.np, ldq = S.ldq;
+#ifdef QPB_TIMING
+    if (threadIdx.x == 0) { for (int i = 0; i < 128; ++i) s_tim[i] = 0; s_tim[128] = clock64(); s_tim2 = s_tim[128]; }
+    __syncthreads();
+#endif
+    __shared__ int s_flag;
+    if (tid == 0) s_flag = 0;
+    const double* Qg = Q + (int64_t)sys * sQ;
+    const double* Gg = G + (int64_t)sys * sG;
+    const double* Ag = (e > 0) ? (A + (int64_t)sys * sA) : nullptr;
+    // ---- stage Q (identity padded) and [A; 0; G; 0] (zero padded): one TMA bulk copy per matrix row (the rows are
+    // contiguous in HBM but padded in shared memory), padding written by the threads meanwhile.
+    __shared__ __align__(8) uint64_t s_bar;
+    const bool tma_rows = ((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(Qg) & 15) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(Gg) & 15) == 0) && (e == 0 || (reinterpret_cast<uintptr_t>(Ag) & 15) == 0);
+    if (tma_rows) {
+        if (tid == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (tid < 32) {
+            const uint32_t rowb = (uint32_t)(n * 8);
+            if (tid == 0) mbar_expect_tx(&s_bar, rowb * (uint32_t)(n + e + m));
+            __syncwarp();
+            for (int r = tid; r < n; r += 32) bulk_g2s(qsm + S.QA + r * ldq, Qg + (int64_t)r * n, rowb, &s_bar);
+            for (int r = tid; r < e; r += 32) bulk_g2s(qsm + S.WA + r * ldq, Ag + (int64_t)r * n, rowb, &s_bar);
+            for (int r = tid; r < m; r += 32) bulk_g2s(qsm + S.WA + (ep + r) * ldq, Gg + (int64_t)r * n, rowb, &s_bar);
+        }
+        for (int r = warp; r < np; r += kThreads / 32)
+            for (int c = lane; c < ldq; c += 32)
+                if (r >= n || c >= n) qsm[S.QA + r * ldq + c] = (r == c) ? 1.0 : 0.0;
+        for (int r = warp; r < msp; r += kThreads / 32) {
+            const bool real = (r < e) || (r >= ep && r < ms);
+            for (int c = lane; c < ldq; c += 32)
+                if (!real || c >= n) qsm[S.WA + r * ldq + c] = 0.0;
+        }
+        mbar_wait(&s_bar, 0);
+    } else {
+        for (int r = warp; r < np; r += kThreads / 32)
+            for (int c = lane; c < ldq; c += 32)
+                qsm[S.QA + r * ldq + c] = (r < n && c < n) ? Qg[(int64_t)r * n + c] : ((r == c && r >= n) ? 1.0 : 0.0);
+        for (int r = warp; r < msp; r += kThreads / 32) {
+            const double* src = nullptr;
+            if (r < e) src = Ag + (int64_t)r * n;
+            else if (r >= ep && r < ms) src = Gg + (int64_t)(r - ep) * n;
+            for (int c = lane; c < ldq; c += 32) qsm[S.WA + r * ldq + c] = (src != nullptr && c < n) ? src[c] : 0.0;
+        }
+    }
+    for (int i = tid; i < np; i += kThreads) qsm[S.aug + i] = 0.0;
+    build_tile_table(reinterpret_cast<uint16_t*>(qsm + S.tab), np >> 3, tid);
+    __syncthreads();
+    QPB_TICK(34);   // staging
+    // ---- 1. Q = L L^T
+    f_chol(S.QA, ldq, np, 0, S.aug, S.tab);
+    QPB_TICK(35);   // chol(Q)
+    for (int i = tid; i < n; i += kThreads) {
+        const double ri = qsm[S.QA + i * ldq + i];                   // reciprocal of L_ii; NaN/inf if a pivot failed
+        if (!(ri > 0.0) || isinf(ri)) s_flag = 1;
+    }
+    // ---- 2. inverted diagonal blocks
+    for (int blk = warp; blk < (np >> 3); blk += kThreads / 32) f_invert8(S.QA + (8 * blk) * ldq + 8 * blk, ldq);
+    __syncthreads();
+    QPB_TICK(36);   // T blocks
+    // ---- 3. W = rows * L^-T, one warp per 8-row tile
+    for (int rt = warp; rt < (msp >> 3); rt += kThreads / 32) f_rows_times_LinvT(S.QA, ldq, np, S.WA, ldq, rt);
+    __syncthreads();
+    QPB_TICK(37);   // W
+    // ---- outputs L (packed lower, true diagonal) and W (compact ms x ldw)
+    double* Lg = Lfac + (int64_t)sys * D.lp;
+    double* Wg = Wfac + (int64_t)sys * ms * D.ldw;
+    double* Kg = Kfac + (int64_t)sys * msp * D.lds;
+    for (int r = warp; r < n; r += kThreads / 32)
+        for (int c = lane; c < r; c += 32) Lg[(r * (r + 1)) / 2 + c] = qsm[S.QA + r * ldq + c];
+    for (int r = tid; r < n; r += kThreads) Lg[(r * (r + 1)) / 2 + r] = 1.0 / qsm[S.QA + r * ldq + r];   // true diagonal
+    if (tid == 0 && (D.lp > n * (n + 1) / 2)) Lg[D.lp - 1] = 0.0;
+    for (int r = warp; r < ms; r += kThreads / 32)
+        for (int c = lane; c < D.ldw; c += 32) Wg[r * D.ldw + c] = (c < n) ? qsm[S.WA + r * ldq + c] : 0.0;
+    if (tid == 0) spd_flag[sys] = s_flag;
+    __syncthreads();
+    QPB_TICK(38);   // write L, W
+    // ---- 4. K = W W^T (lower tiles), into the Q area with leading dimension lds
+    {
+        const int g = lane >> 2, q = lane & 3;
+        const int nts = msp >> 3;
+        const int T = nts * (nts + 1) / 2;
+        const int lds = D.lds;
+        for (int i = tid; i < msp * lds; i += kThreads) qsm[S.QA + i] = 0.0;      // (also clears the upper triangle)
+        __syncthreads();
+        for (int t = warp; t < T; t += kThreads / 32) {
+            int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while (ti * (ti + 1) / 2 > t) --ti;
+            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+            const int tj = t - ti * (ti + 1) / 2;
+            const double* pa = qsm + S.WA + (8 * ti + g) * ldq + q;
+            const double* pb = qsm + S.WA + (8 * tj + g) * ldq + q;
+            double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;                         // two accumulator chains
+            for (int kk = 0; kk < np; kk += 8) {
+                dmma884(c0, c1, pa[kk], pb[kk]);
+                dmma884(d0, d1, pa[kk + 4], pb[kk + 4]);
+            }
+            const int rr = 8 * ti + g, cc = 8 * tj + 2 * q;
+            double v0 = c0 + d0, v1 = c1 + d1;
+            // dummy equality rows and pad rows: unit diagonal
+            if (rr == cc && ((rr >= e && rr < ep) || rr >= ms)) v0 += 1.0;
+            if (rr == cc + 1 && ((rr >= e && rr < ep) || rr >= ms)) v1 += 1.0;
+            if (cc <= rr) qsm[S.QA + rr * lds + cc] = v0;
+            if (cc + 1 <= rr) qsm[S.QA + rr * lds + cc + 1] = v1;
+        }
+    }
+    __syncthreads();
+    QPB_TICK(39);   // K = W W^T
+    if (ep > 0) {
+        double* RA = qsm + S.QA;
+        chol_partial(RA, D.lds, ms, 0, ep, nullptr, 0, 0, qsm + S.aug, nullptr, tid, kThreads);
+        for (int i = tid; i < ms * D.lds; i += kThreads) {                         // DMMA tiles spill into the upper triangle
+            const int r = i / D.lds, c = i - r * D.lds;
+            if (c > r) RA[i] = 0.0;
+        }
+        __syncthreads();
+        for (int i = tid; i < ep; i += kThreads) RA[i * D.lds + i] = 1.0 / RA[i * D.lds + i];   // reciprocal-diagonal convention
+        __syncthreads();
+    }
+    QPB_TICK(45);   // partial chol of the equality block
+    for (int i = tid; i < msp * D.lds; i += kThreads) Kg[i] = qsm[S.QA + i];
+    QPB_TICK(46);   // write K
+#ifdef QPB_TIMING
+    if (tid == 0 && sys == 0) for (int i = 0; i < 128; ++i) g_tim[i] = s_tim[i];
+#endif
+}
+
 // fp64 FMA issue-rate probe: 8 independent DFMA chains per thread (roofline denominator for bench.py)
 __global__ void k_dfma_probe(int iters, double* out) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
@@ -1201,12 +1363,15 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
     KDims D = dims_of(plan);
     const int64_t fast_doubles = (int64_t)fk::fast_smem_doubles(D);
     const bool setup_fits = (setup_mat + setup_vec) * 8 <= kMaxSmem;
-    const bool fast_ok = setup_fits && fast_doubles * 8 <= kMaxSmem && nineq <= 8 * kCholMaxTiles && (msp - plan->neq_pad) / 8 >= 1;
+    const bool fast_ok = setup_fits && fast_doubles * 8 <= kMaxSmem && nineq <= 8 * kCholMaxTiles && (msp - plan->neq_pad) / 8 >= 1 && msp <= 224;
     const bool fits = setup_fits && (solve_mat_s + solve_vec) * 8 <= kMaxSmem;
+    const fk::SLayout SL = fk::setup_layout(D);
+    const bool setup_fast_ok = fast_ok && nz <= 8 * kCholMaxTiles && (int64_t)SL.total * 8 <= kMaxSmem;
     plan->fast = fast_ok ? 1 : 0;
+    plan->setup_fast = setup_fast_ok ? 1 : 0;
     plan->smem_resident = (fast_ok || fits) ? 1 : 0;
     if (setup_fits && (fast_ok || fits)) {
-        plan->setup_smem_bytes = (setup_mat + setup_vec) * 8;
+        plan->setup_smem_bytes = setup_fast_ok ? (int64_t)SL.total * 8 : (setup_mat + setup_vec) * 8;
         plan->solve_smem_bytes = fast_ok ? fast_doubles * 8 : (solve_mat_s + solve_vec) * 8;
         plan->setup_scratch_elems = 0;
         plan->solve_scratch_elems = 0;
@@ -1228,7 +1393,11 @@ int qpb200_pre_factor_kkt(const qpb200_plan* plan, int nsys, const double* Q, in
     if (plan->neq > 0 && !A) return QPB200_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     KDims D = dims_of(plan);
-    if (plan->smem_resident) {
+    if (plan->setup_fast) {
+        int rc = set_smem(k_setup_fast, plan->setup_smem_bytes);
+        if (rc) return rc;
+        k_setup_fast<<<nsys, kThreads, plan->setup_smem_bytes, st>>>(D, Q, sQ, G, sG, A, sA, Lfac, Wfac, Kfac, spd_flag);
+    } else if (plan->smem_resident) {
         int rc = set_smem(k_setup<true>, plan->setup_smem_bytes);
         if (rc) return rc;
         k_setup<true><<<nsys, kThreads, plan->setup_smem_bytes, st>>>(D, Q, sQ, G, sG, A, sA, Lfac, Wfac,
@@ -1373,11 +1542,11 @@ int qpb200_backward(const qpb200_plan* plan, int nbatch, const double* dl_dzhat,
 #ifdef QPB_TIMING
 int qpb200_debug_timing(long long* host64, int reset) {
     if (reset) {
-        long long z[64] = {0};
+        long long z[128] = {0};
         CK(cudaMemcpyToSymbol(qpb::fast::g_tim, z, sizeof(z)));
         return QPB200_OK;
     }
-    CK(cudaMemcpyFromSymbol(host64, qpb::fast::g_tim, 64 * sizeof(long long)));
+    CK(cudaMemcpyFromSymbol(host64, qpb::fast::g_tim, 128 * sizeof(long long)));
     return QPB200_OK;
 }
 #endif

@@ -17,7 +17,7 @@ f = QPFunction(verbose=-1, check_Q_spd=False)
 f(t["Q"], t["p"], t["G"], t["h"], t["A"], t["b"]); torch.cuda.synchronize()
 lib.qpb200_debug_timing(None, 1)
 f(t["Q"], t["p"], t["G"], t["h"], t["A"], t["b"]); torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 64)()
+buf = (ctypes.c_longlong * 128)()
 lib.qpb200_debug_timing(buf, 0)
 torch.cuda.synchronize(); it = int(f.last_solve().iters.cpu()[0]); print('iters', f.last_solve().iters.cpu()[:8].tolist(), 'resid', f.last_solve().best_resid.cpu()[:3].tolist())
 names = {0: "make_ctx (TMA W,L)", 1: "load vectors", 2: "whiten", 3: "loop misc/update (prev)", 4: "matvec_cols (r~x)", 5: "matvec_rows2", 6: "residual elementwise", 7: "tri_norm2", 8: "reduce_sum4",
@@ -26,6 +26,11 @@ names = {0: "make_ctx (TMA W,L)", 1: "load vectors", 2: "whiten", 3: "loop misc/
          40: "[warp1] gap", 41: "[warp1] S_k rows", 42: "[warp1] named barrier wait", 43: "[warp1] U_k update", 44: "[warp1] step barrier wait", 30: "wait K copy", 31: "diag add + barrier", 32: "chol exit", 33: "trsv_bwd (aff)"}
 tot = sum(buf)
 print("QP 0 of block 0: %d iterations; total %d cycles (%.1f us @1.965GHz); per iteration %.0f" % (it, tot, tot / 1965.0, tot / (it + 1)))
-for i in range(64):
+for i in range(48):
     if buf[i]:
         print("%2d %-34s %9d cyc  %5.1f%%   per-iter %7.0f" % (i, names.get(i, "?"), buf[i], 100.0 * buf[i] / tot, buf[i] / (it + 1)))
+
+nf = it + 1
+print("per Cholesky step k (cycles per factorization): S_k[w1]  U_k[w1] | s_k[w0]  F_k+1[w0]  wait[w0]")
+for k in range(13):
+    print("%2d  %6.0f %6.0f | %6.0f %6.0f %6.0f" % (k, buf[64 + k] / nf, buf[48 + k] / nf, buf[96 + k] / nf, buf[80 + k] / nf, buf[112 + k] / nf))
