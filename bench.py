@@ -95,11 +95,13 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def settle(step, min_steps, chunk, max_steps=400):
+def settle(step, min_steps, chunk, max_steps=None):
     """Warm-up: at least `min_steps` steps, then keep going (in chunks) until the CUDA caching allocator has stopped
     growing. On these boxes a fresh cudaMalloc of a 10-20 MB block costs ~10 ms and synchronises, and the pool of a
     loop that allocates ~70 MB per step keeps growing for the first few dozen steps; timing before it has settled
     measures cudaMalloc, not the solver. Returns the number of warm-up steps run."""
+    if max_steps is None:
+        max_steps = env_int("QPB_BENCH_MAX_SETTLE", 400)      # (lowered only for runs under ncu)
     done = 0
     while done < min_steps:
         step(done); done += 1
