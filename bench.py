@@ -190,8 +190,44 @@ def run_b200(args, rank, world, local_rank):
         except Exception as exc:                                  # noqa: BLE001
             sys.stderr.write("bench: CUDA graph capture failed (%s); using the eager loop\n" % str(exc)[:200])
             torch.cuda.synchronize()
-    for i in range(args.steps):            # untimed rehearsal of the timed loop: same run-ahead, same allocation pattern
-        step(warm_done + i)
+    # `value`: K steps with the inputs resident in HBM. A step's kernels have 128 CTAs (one QP each) on 148 SMs and
+    # a QP leaves its SM as soon as it has converged (12 Newton iterations on average, 16-18 for the slowest QP of
+    # a batch), so a single stream idles most SMs during the tail of every forward kernel. As in a serving loop
+    # (and as in the e2e leg below) consecutive steps alternate between INFLIGHT CUDA streams: the next batch's
+    # CTAs take over the SMs the previous batch has already released. Every step is still one complete
+    # forward + backward over its own batch; the single-stream figure is reported next to it (config.serial_*).
+    inflight = max(1, env_int("QPB_BENCH_INFLIGHT", 2))
+    vstreams = [torch.cuda.Stream(device=dev) for _ in range(inflight)]
+
+    def timed_window(nsteps, first, streams):
+        """Device time of `nsteps` steps issued round-robin on `streams` (None: the current stream)."""
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if streams is None:
+            for i in range(nsteps):
+                step(first + i)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1)
+        ends = []
+        for st_ in streams:
+            st_.wait_event(e0)
+        for i in range(nsteps):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                step(first + i)
+        for st_ in streams:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(st_)
+            ends.append(e1)
+        torch.cuda.synchronize()
+        return max(e0.elapsed_time(e1) for e1 in ends)
+
+    use_streams = vstreams if inflight > 1 else None
+    timed_window(args.steps, warm_done, use_streams)       # untimed rehearsal: same run-ahead, same allocation pattern
+    warm_done += args.steps
+    serial_ms = timed_window(args.steps, warm_done, None)  # informational: one stream, steps strictly back to back
     warm_done += args.steps
     torch.cuda.synchronize()
     if world > 1:
@@ -199,14 +235,7 @@ def run_b200(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record()
-    for i in range(args.steps):
-        step(warm_done + i)
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
+    ms = timed_window(args.steps, warm_done, use_streams)
     clocks = sampler.stop() if sampler else None
     iters_mean = float((last_iters if launch_mode == "cuda_graph" else f.last_solve().iters).float().mean())
     if world > 1:
@@ -216,9 +245,11 @@ def run_b200(args, rank, world, local_rank):
         torch.distributed.barrier()
 
     # ---- e2e: the same step through QPFunction with HOST (pinned) buffers, H2D + D2H inside the timed region.
-    # Two steps are kept in flight on alternating CUDA streams (double buffering, as a serving loop would):
-    # step i's D2H and step i+1's H2D overlap with compute; every step still moves all of its own bytes.
-    NS = 2
+    # NS steps are kept in flight on NS CUDA streams (as a serving loop would): a step is H2D (~0.5 ms), compute
+    # (~0.6 ms), D2H (~0.5 ms) in sequence on its stream, so two streams leave the PCIe link idle a third of the
+    # time; with three the link (full duplex, ~33 GB/s each way measured) or the SMs are the limit. Every step
+    # still moves all of its own bytes.
+    NS = max(1, env_int("QPB_BENCH_E2E_INFLIGHT", 3))
     hb = make_batches(dev, 1000 * rank, NS, pinned_host=True)
     host_out = [{k: torch.empty(s, dtype=torch.float64).pin_memory()
                  for k, s in (("z", (B, n)), ("dQ", (B, n, n)), ("dp", (B, n)), ("dG", (B, m, n)), ("dh", (B, m)))}
@@ -246,7 +277,7 @@ def run_b200(args, rank, world, local_rank):
 
     for st_ in streams:
         st_.wait_stream(torch.cuda.current_stream())
-    ksteps = max(6, args.steps // 2 * 2)
+    ksteps = max(2 * NS, args.steps // NS * NS)
     settle(e2e_step, max(4, args.warmup), 2 * NS)
     for i in range(ksteps):                # untimed rehearsal (see above)
         e2e_step(i)
@@ -289,6 +320,7 @@ def run_b200(args, rank, world, local_rank):
     Qc, Gc, pc, hc = (t[k].detach().contiguous() for k in ("Q", "G", "p", "h"))
     _lib.check(lib.qpb200_pre_factor_kkt(ctypes.byref(plan), B, P(Qc), n * n, P(Gc), m * n, None, 0,
                                          P(L), P(W), P(K), P(spd), None, st))
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     kt = []
     for i in range(8):
         ev0.record()
@@ -333,10 +365,11 @@ def run_b200(args, rank, world, local_rank):
         "data": "synthetic (seeded prof-linear.py generator)", "impl": "b200",
         "config": {"workload": WORKLOAD, "per_gpu_batch": B, "options": "eps=1e-12 maxIter=20 notImprovedLim=3 verbose=-1 check_Q_spd=False",
                    "l2": "inputs rotate over %d independent batches (%.0f MB > 126 MB L2)" % (NCOPIES, NCOPIES * h2d / 1e6),
-                   "mean_newton_iters": iters_mean, "launch": launch_mode},
+                   "mean_newton_iters": iters_mean, "launch": launch_mode, "steps_in_flight": inflight,
+                   "serial_ms_per_step": serial_ms / args.steps, "serial_value": total_qps / (serial_ms * 1e-3)},
         "e2e": {"value": world * B * ksteps / (e2e_ms * 1e-3), "unit": "QPs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": ksteps, "windows_ms": windows,
-                "api": "qpth_b200.QPFunction; per step: H2D of Q,p,G,h from pinned host memory, fwd, bwd, D2H of z* and all gradients; two steps in flight on alternating CUDA streams"},
+                "api": "qpth_b200.QPFunction; per step: H2D of Q,p,G,h from pinned host memory, fwd, bwd, D2H of z* and all gradients; %d steps in flight on %d CUDA streams" % (NS, NS), "steps_in_flight": NS},
         "gpu_launches": 3 * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_forward_fast", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

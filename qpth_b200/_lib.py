@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqpth_b200.so")
+# QPB200_LIB: development override (A/B builds of the kernels); the product is the in-tree libqpth_b200.so
+LIB_PATH = os.environ.get("QPB200_LIB") or os.path.join(_HERE, "libqpth_b200.so")
 
 c_double_p = ctypes.c_void_p
 c_int_p = ctypes.c_void_p

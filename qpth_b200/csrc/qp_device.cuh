@@ -26,13 +26,19 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// Both reductions start with __syncwarp(): they are called after loops whose trip count differs between lanes
+// (for (i = tid; i < ms; ...)). Without it the compiler cannot prove convergence and the shuffles go through their
+// divergent-warp fallback (BRA.DIV -> WARPSYNC.COLLECTIVE per shuffle): measured 2.7k cycles for two sums instead
+// of ~300 (profiles/r1d_phase_*).
 __device__ __forceinline__ double warp_sum(double v) {
+    __syncwarp();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 // min that propagates nothing special: callers only feed non-NaN candidates or +inf
 __device__ __forceinline__ double warp_min(double v) {
+    __syncwarp();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
@@ -84,8 +90,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
-// Issue a contiguous copy as 16 KB chunks spread over the lanes of one warp. The barrier must already
-// have been armed (mbar_expect_tx) with the total byte count of everything that will land on it.
+// Issue a contiguous copy as 16 KB chunks from ONE thread (rolled loop). The barrier must already have been armed
+// (mbar_expect_tx) with the total byte count of everything that will land on it. (cp.async.bulk takes uniform
+// operands: issued per lane, every call site became a serialised elect loop and ~2 KB of SASS.)
+__device__ __forceinline__ void bulk_issue_thread(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    const uint32_t chunk = 16384;
+#pragma unroll 1
+    for (uint32_t off = 0; off < bytes; off += chunk) {
+        const uint32_t nb = (bytes - off < chunk) ? (bytes - off) : chunk;
+        bulk_g2s((char*)dst_smem + off, (const char*)src_gmem + off, nb, bar);
+    }
+}
+// (lane-parallel variant, kept for the generic kernels)
 __device__ __forceinline__ void bulk_issue_warp(void* dst_smem, const void* src_gmem, uint32_t bytes,
                                                 uint64_t* bar, int lane) {
     const uint32_t chunk = 16384;

@@ -181,16 +181,10 @@ __device__ __noinline__ void f_chol_chain(int A, int ld, int n, int c0) {
     const int nts = (n - c0) >> 3;
     double* M = qsm + A;
     double Lk[36];                                           // the current diagonal block stays in registers
-    f_load_lower8(M + c0 * ld + c0, ld, Lk);
-    __syncwarp();
-    f_factor8_regs(Lk);                                                               // F_0
-    if (lane == 0) f_store_lower8(M + c0 * ld + c0, ld, Lk);
-    QPB_TICK(20);
-    __syncthreads();
-    QPB_TICK(21);
-    for (int k = 0; k < nts; ++k) {
+    // k = -1 is the prologue step (F_0 only): ONE instance of the unrolled 8x8 factorization in the code.
+    for (int k = -1; k < nts; ++k) {
         const int k0 = c0 + 8 * k;
-        if (k + 1 < nts) {
+        if (k >= 0 && k + 1 < nts) {
             // ---- s_k: the 8 panel rows of block k+1 (lanes 0..7), L_kk still in registers from F_k
             if (lane < 8) {
                 double a[8];
@@ -212,15 +206,17 @@ __device__ __noinline__ void f_chol_chain(int A, int ld, int n, int c0) {
             *reinterpret_cast<double2*>(pd) = cv;
             __syncwarp();
             QPB_TICK(24);
+        }
+        if (k + 1 < nts) {
             f_load_lower8(M + (k0 + 8) * ld + k0 + 8, ld, Lk);
             __syncwarp();                                                             // all lanes have read the tile
             f_factor8_regs(Lk);                                                       // F_{k+1}
             if (lane == 0) f_store_lower8(M + (k0 + 8) * ld + k0 + 8, ld, Lk);
-            QPB_TICK(80 + k);   // F_{k+1}, per step
+            if (k >= 0) QPB_TICK(80 + k);   // F_{k+1}, per step
         }
         QPB_TICK(26);
         __syncthreads();
-        QPB_TICK(112 + k);      // chain warp waiting for the update warps, per step
+        if (k >= 0) QPB_TICK(112 + k);      // chain warp waiting for the update warps, per step
     }
 }
 
@@ -237,18 +233,18 @@ __device__ __noinline__ void f_chol_update(int A, int ld, int n, int c0, int aug
     double* M = qsm + A;
     const int uw = (warp == 4) ? -1 : (warp < 4 ? warp - 1 : warp - 2);
     double C[kCholMaxOff][2];
-    int tj_of[kCholMaxOff];                                  // column block of each owned tile (-1: empty slot)
-    int offA[kCholMaxOff], offB[kCholMaxOff];                // fragment base offsets (rows of block ti / tj)
+    // per slot only the packed tile id (ti << 8 | tj, -1: empty) lives in a register; fragment offsets are two IMADs
+    // away. (Arrays of precomputed offsets pushed this function into local memory: 26 STL + 4 LDL per tile pair.)
+    int tt_of[kCholMaxOff];
+    const int gq = (c0 + g) * ld + q;
     if (uw >= 0) {
 #pragma unroll
         for (int s = 0; s < kCholMaxOff; ++s) {
             const int idx = s * 6 + uw;
             const bool ok = idx < noff;
             const int tt = ok ? tab[idx] : 0;
-            tj_of[s] = ok ? (tt & 255) : -1;
-            offA[s] = (c0 + 8 * (tt >> 8) + g) * ld + q;
-            offB[s] = (c0 + 8 * (tt & 255) + g) * ld + q;
-            const double2 v = ok ? *reinterpret_cast<const double2*>(M + (c0 + 8 * (tt >> 8) + g) * ld + c0 + 8 * (tt & 255) + 2 * q)
+            tt_of[s] = ok ? tt : -1;
+            const double2 v = ok ? *reinterpret_cast<const double2*>(M + gq + q + 8 * (tt >> 8) * ld + c0 + 8 * (tt & 255))
                                  : make_double2(0.0, 0.0);
             C[s][0] = v.x; C[s][1] = v.y;
         }
@@ -282,22 +278,25 @@ __device__ __noinline__ void f_chol_update(int A, int ld, int n, int c0, int aug
 #pragma unroll
                 for (int s = kCholMaxOff - 1; s >= 0; s -= 2) {
                     const int s1 = s, s2 = (s - 1 >= 0) ? s - 1 : 0;
-                    const bool act1 = tj_of[s1] > k;                           // warp-uniform
-                    const bool act2 = (s - 1 >= 0) && (tj_of[s2] > k);
+                    const int t1 = tt_of[s1], t2 = tt_of[s2];
+                    const bool act1 = (t1 & 255) > k && t1 >= 0;               // warp-uniform
+                    const bool act2 = (s - 1 >= 0) && (t2 & 255) > k && t2 >= 0;
                     if (!act1 && !act2) continue;
+                    const double* pa1 = M + gq + 8 * (t1 >> 8) * ld + k0;
+                    const double* pb1 = M + gq + 8 * (t1 & 255) * ld + k0;
+                    const double* pa2 = M + gq + 8 * (t2 >> 8) * ld + k0;
+                    const double* pb2 = M + gq + 8 * (t2 & 255) * ld + k0;
                     double a10 = 0, a11 = 0, b10 = 0, b11 = 0, a20 = 0, a21 = 0, b20 = 0, b21 = 0;
-                    if (act1) { const double* pa = M + offA[s1] + k0; const double* pb = M + offB[s1] + k0;
-                                a10 = pa[0]; a11 = pa[4]; b10 = pb[0]; b11 = pb[4]; }
-                    if (act2) { const double* pa = M + offA[s2] + k0; const double* pb = M + offB[s2] + k0;
-                                a20 = pa[0]; a21 = pa[4]; b20 = pb[0]; b21 = pb[4]; }
+                    if (act1) { a10 = pa1[0]; a11 = pa1[4]; b10 = pb1[0]; b11 = pb1[4]; }
+                    if (act2) { a20 = pa2[0]; a21 = pa2[4]; b20 = pb2[0]; b21 = pb2[4]; }
                     if (act1) dmma884(C[s1][0], C[s1][1], -a10, b10);
                     if (act2) dmma884(C[s2][0], C[s2][1], -a20, b20);
                     if (act1) dmma884(C[s1][0], C[s1][1], -a11, b11);
                     if (act2) dmma884(C[s2][0], C[s2][1], -a21, b21);
-                    if (act1 && tj_of[s1] == k + 1)            // this tile belongs to the next panel: publish it
-                        *reinterpret_cast<double2*>(M + offA[s1] + q + c0 + 8 * (k + 1)) = make_double2(C[s1][0], C[s1][1]);
-                    if (act2 && tj_of[s2] == k + 1)
-                        *reinterpret_cast<double2*>(M + offA[s2] + q + c0 + 8 * (k + 1)) = make_double2(C[s2][0], C[s2][1]);
+                    if (act1 && (t1 & 255) == k + 1)           // this tile belongs to the next panel: publish it
+                        *reinterpret_cast<double2*>(M + gq + q + 8 * (t1 >> 8) * ld + c0 + 8 * (k + 1)) = make_double2(C[s1][0], C[s1][1]);
+                    if (act2 && (t2 & 255) == k + 1)
+                        *reinterpret_cast<double2*>(M + gq + q + 8 * (t2 >> 8) * ld + c0 + 8 * (k + 1)) = make_double2(C[s2][0], C[s2][1]);
                 }
                 // diagonal tiles s > k+1 are updated in place in shared memory, spread over the update warps
                 for (int s = k + 2 + uw; s < nts; s += 6) {
@@ -395,6 +394,188 @@ __device__ __noinline__ void f_trsv_bwd(int A, int ld, int n, int u, int w) {
     }
 }
 
+// ---- product form of the factor: substitution without an intra-block chain -------------------------------
+// f_to_pform rewrites a factored matrix (diagonal blocks: strictly lower = L, diagonal = 1/L_cc) as
+//   T_k  = L_kk^-1      strictly lower part stored TRANSPOSED in the upper triangle of diagonal tile k
+//                       (T_k[j][c] at tile[c][j], j > c; its diagonal is the reciprocal diagonal already there),
+//   P_ik = L_ik T_k     in place of every tile below the diagonal.
+// Then   L y = b   :  y_k = T_k b_k,  b_i -= P_ik b_k  (b = running right-hand side), and
+//        L^T w = u :  u'_k = T_k^T u_k,  w_k = u'_k - sum_{i>k} P_ik^T w_i,
+// i.e. one 8-term dot product per thread and block step; the 8-long substitution chain of f_trsv_* (8 x (mul + fma)
+// dependent, redone by every thread) is gone and y_k is off the critical path. Costs one pass over the factor
+// (36 FMAs per row and block) per factorization; pays for itself with the three solves that follow.
+#ifndef QPB_PFORM
+#define QPB_PFORM 1
+#endif
+
+// Upper triangle incl. diagonal of the 8x8 tile at Mb: T[QPB_LIDX(j, c)] = Mb[c][j], j >= c  (= T_k[j][c]).
+__device__ __forceinline__ void f_load_upper8(const double* Mb, int ld, double (&T)[36]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int j = c & ~1; j < 8; j += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(Mb + c * ld + j);
+            if (j >= c) T[QPB_LIDX(j, c)] = v.x;
+            T[QPB_LIDX(j + 1, c)] = v.y;
+        }
+}
+
+// All blocks of the n x n factor at A (n multiple of 8, n <= 8 * 32). Call with all threads; ends with a barrier.
+__device__ __noinline__ void f_to_pform(int A, int ld, int n) {
+    QPB_SMEM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* M = qsm + A;
+    const int nts = n >> 3;
+    // (i) T_k: 8 lanes per diagonal block, lane c computes column c of T_k (zeros above the diagonal of T).
+    // Reads touch the lower triangle only, writes the strictly upper one: no hazard between the lanes of a block.
+    if (tid < 8 * nts) {
+        const int k0 = tid & ~7, c = tid & 7;
+        double* Mb = M + k0 * ld + k0;
+        double Lk[36], Tc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int cc = 0; cc <= r; cc += 2) {
+                if (cc + 1 <= r) {
+                    const double2 v = *reinterpret_cast<const double2*>(Mb + r * ld + cc);
+                    Lk[QPB_LIDX(r, cc)] = v.x; Lk[QPB_LIDX(r, cc + 1)] = v.y;
+                } else {
+                    Lk[QPB_LIDX(r, cc)] = Mb[r * ld + cc];
+                }
+            }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int j = 0; j < r; ++j) sacc = fma(Lk[QPB_LIDX(r, j)], Tc[j], sacc);
+            Tc[r] = (r < c) ? 0.0 : ((r == c) ? Lk[QPB_LIDX(r, r)] : -Lk[QPB_LIDX(r, r)] * sacc);
+        }
+#pragma unroll
+        for (int r = 1; r < 8; ++r)
+            if (r > c) Mb[c * ld + r] = Tc[r];
+    }
+    __syncthreads();
+    QPB_TICK(17);   // T_k blocks
+    // (ii) P_ik = L_ik T_k on the fp64 tensor pipe: one 8x8 tile = 2 DMMAs, tiles dealt round-robin to the warps.
+    // (The FMA version - one row per lane, T_k reloaded per work item - was LSU-bound: 4.3k cycles per factorization.)
+    {
+        const int g = lane >> 2, q = lane & 3;
+        int item = 0;
+#pragma unroll 1
+        for (int k = 0; k + 1 < nts; ++k) {
+            const int k0 = 8 * k;
+            const double* Tb = M + (k0 + g) * ld + k0;                         // row g of diagonal tile k
+            // B fragment: T_k[kk][g], kk = q (slice 0), q + 4 (slice 1); T_k[kk][nn] = tile[nn][kk] for kk >= nn
+            const double b0 = (q >= g) ? Tb[q] : 0.0, b1 = (q + 4 >= g) ? Tb[q + 4] : 0.0;
+#pragma unroll 1
+            for (int ti = k + 1; ti < nts; ++ti, ++item) {
+                if ((item & 7) != warp) continue;
+                double* rowp = M + (8 * ti + g) * ld + k0;
+                const double a0 = rowp[q], a1 = rowp[q + 4];
+                double d0 = 0.0, d1 = 0.0;
+                dmma884(d0, d1, a0, b0);
+                dmma884(d0, d1, a1, b1);
+                *reinterpret_cast<double2*>(rowp + 2 * q) = make_double2(d0, d1);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// L y = b over ALL blocks of a product-form factor: u = y. Thread tid owns entry tid of the running right-hand
+// side in a register; a block of 8 entries is published to b[] when it becomes final, and y_k = T_k b_k is taken
+// for all blocks at once after the sweep (the b_k stay in place). b destroyed, b != u. One barrier per block
+// step; the P row of the NEXT step is fetched before it.
+// (First version: 8 "solver" threads computed y_k inside every step - 8 dependent LDS->FMA links, ~360 cycles,
+// longer than the row update it was supposed to hide behind: 540 cycles per step measured.)
+__device__ __noinline__ void f_ptrsv_fwd(int A, int ld, int n, int b, int u) {
+    QPB_SMEM;
+    const int tid = threadIdx.x;
+    const double* M = qsm + A;
+    const bool mine = tid >= 8 && tid < n;
+    double acc = mine ? qsm[b + tid] : 0.0;
+    double row[8];
+    if (mine) f_ld8(M + tid * ld, row);
+#pragma unroll 1
+    for (int k0 = 0; k0 + 8 < n; k0 += 8) {
+        if (tid >= k0 + 8 && tid < n) {
+            double y[8];
+            f_ld8(qsm + b + k0, y);
+            double s1 = row[1] * y[1];
+            acc = fma(-row[0], y[0], acc); s1 = fma(row[3], y[3], s1);
+            acc = fma(-row[2], y[2], acc); s1 = fma(row[5], y[5], s1);
+            acc = fma(-row[4], y[4], acc); s1 = fma(row[7], y[7], s1);
+            acc = fma(-row[6], y[6], acc);
+            acc -= s1;
+            if (tid < k0 + 16) qsm[b + tid] = acc;
+            else f_ld8(M + tid * ld + k0 + 8, row);          // next step's P row (static data: no hazard)
+        }
+        __syncthreads();
+    }
+    if (tid < n) {                                           // y = blockdiag(T_k) b: T_k[r][c] = tile[c][r], c <= r
+        const int k0 = tid & ~7, r = tid & 7;
+        double y[8], t[8];
+        f_ld8(qsm + b + k0, y);
+        const double* Tb = M + k0 * ld + k0 + r;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) t[c] = Tb[c * ld];       // column r of the tile (rows > r hold L: masked below)
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+            s0 = fma((c <= r) ? t[c] : 0.0, y[c], s0);
+            s1 = fma((c + 1 <= r) ? t[c + 1] : 0.0, y[c + 1], s1);
+        }
+        qsm[u + tid] = s0 + s1;
+    }
+    __syncthreads();
+}
+
+// L^T w = u for a product-form factor. Thread tid owns w[tid]. u is only read. u != w.
+__device__ __noinline__ void f_ptrsv_bwd(int A, int ld, int n, int u, int w) {
+    QPB_SMEM;
+    const int tid = threadIdx.x;
+    const double* M = qsm + A;
+    double acc = 0.0;
+    if (tid < n) {                                           // u'_k = T_k^T u_k: row c of the (upper-stored) tile
+        const int k0 = tid & ~7, c = tid & 7;
+        double t[8], uu[8];
+        f_ld8(M + (k0 + c) * ld + k0, t);
+        f_ld8(qsm + u + k0, uu);
+        double s1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) {
+            acc = fma((r >= c) ? t[r] : 0.0, uu[r], acc);
+            s1 = fma((r + 1 >= c) ? t[r + 1] : 0.0, uu[r + 1], s1);
+        }
+        acc += s1;
+        if (tid >= n - 8) qsm[w + tid] = acc;
+    }
+    double col[8];
+    if (tid < n - 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) col[c] = M[(n - 8 + c) * ld + tid];
+    }
+    __syncthreads();
+    for (int k0 = n - 8; k0 > 0; k0 -= 8) {
+        if (tid < k0) {
+            double y[8];
+            f_ld8(qsm + w + k0, y);
+            double s1 = col[1] * y[1];
+            acc = fma(-col[0], y[0], acc); s1 = fma(col[3], y[3], s1);
+            acc = fma(-col[2], y[2], acc); s1 = fma(col[5], y[5], s1);
+            acc = fma(-col[4], y[4], acc); s1 = fma(col[7], y[7], s1);
+            acc = fma(-col[6], y[6], acc);
+            acc -= s1;
+            if (tid >= k0 - 8) qsm[w + tid] = acc;
+            else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) col[c] = M[(k0 - 8 + c) * ld + tid];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Invert a factored 8x8 diagonal block (strictly lower = L, diagonal = 1/L_cc): T = L_kk^-1. T's strictly
 // lower part is written TRANSPOSED into the (unused) upper triangle of the block; its diagonal is the
 // reciprocal diagonal already there. One lane does the work (pre_factor_kkt only; off the Newton loop).
@@ -469,44 +650,40 @@ __device__ __noinline__ void f_unwhiten(int Lp, int n, int dinvL, int u, int w) 
 }
 
 // ---- mat-vecs with W (rows x cols, ld) ---------------------------------------------------------------------
-// y1 = W x1, y2 = W x2 (4 lanes per row, conflict free for ld % 8 == 4). The slices of x1/x2 a lane needs are
-// cached in registers, so the loop streams W only (one LDS per two FMAs instead of three).
+// CODE SIZE is a first-class constraint in this file: the Newton loop runs ~150 KB of SASS once per iteration in
+// the first version, against a 32 KB L1.5 instruction cache, and ncu/clock64 accounting showed every cold phase
+// costing ~0.5 cycle per byte of code it touches (a 16-26 KB single-warp routine: 15-20k cycles for ~1000
+// executed instructions). Loops below are therefore rolled (unroll 1-2) and long expansions (fp64 divide, sqrt,
+// reductions) are shared subroutines.
+//
+// y1 = W x1 (, y2 = W x2): 2 lanes per row, 128 rows per pass; lane h of a pair takes the 16-byte column pairs
+// 4k + 2h, so a quarter-warp's LDS.128 hits 8 distinct 16-byte bank groups for any ld % 8 == 4.
 template <bool kTwo>
 __device__ __forceinline__ void f_matvec_rows_impl(int W, int ld, int rows, int cols, int x1, int x2, int y1, int y2) {
     QPB_SMEM;
-    const int tid = threadIdx.x, q4 = tid >> 2, l = tid & 3;
-    constexpr int kMaxK = 26;                                // cols <= 104
-    if (cols > 4 * kMaxK) {
-        matvec_rows<kTwo>(qsm + W, ld, rows, cols, qsm + x1, kTwo ? qsm + x2 : nullptr, qsm + y1, kTwo ? qsm + y2 : nullptr, tid, kNT);
-        return;
-    }
-    double xa[kMaxK], xb[kMaxK];
-#pragma unroll
-    for (int k = 0; k < kMaxK; ++k) {
-        const int c = l + 4 * k;
-        xa[k] = (c < cols) ? qsm[x1 + c] : 0.0;
-        xb[k] = (kTwo && c < cols) ? qsm[x2 + c] : 0.0;
-    }
-    for (int rb = 0; rb < rows; rb += kNT / 4) {
-        const int r = rb + q4;
+    const int tid = threadIdx.x, h = tid & 1;
+    for (int rb = 0; rb < rows; rb += kNT / 2) {
+        const int r = rb + (tid >> 1);
         const bool ok = r < rows;
-        const double* a = qsm + W + (ok ? r : 0) * ld + l;
+        const double* a = qsm + W + (ok ? r : 0) * ld + 2 * h;
         double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
-#pragma unroll
-        for (int k = 0; k < kMaxK; k += 2) {
-            const double w0 = (ok && l + 4 * k < cols) ? a[4 * k] : 0.0;
-            const double w1 = (ok && l + 4 * k + 4 < cols) ? a[4 * k + 4] : 0.0;
-            s1a = fma(w0, xa[k], s1a); s1b = fma(w1, xa[k + 1], s1b);
-            if (kTwo) { s2a = fma(w0, xb[k], s2a); s2b = fma(w1, xb[k + 1], s2b); }
+#pragma unroll 2
+        for (int c = 2 * h; c < cols; c += 4, a += 4) {
+            const double2 w = *reinterpret_cast<const double2*>(a);
+            const double2 u = *reinterpret_cast<const double2*>(qsm + x1 + c);
+            const bool hi = c + 1 < cols;                     // odd cols: neither W[r][cols] nor x[cols] is ours
+            const double wy = hi ? w.y : 0.0;
+            s1a = fma(w.x, u.x, s1a); s1b = fma(wy, hi ? u.y : 0.0, s1b);
+            if (kTwo) {
+                const double2 v = *reinterpret_cast<const double2*>(qsm + x2 + c);
+                s2a = fma(w.x, v.x, s2a); s2b = fma(wy, hi ? v.y : 0.0, s2b);
+            }
         }
         double s1 = s1a + s1b, s2 = s2a + s2b;
+        __syncwarp();                                        // converged warp -> the shuffles take their fast path
         s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-        if (kTwo) {
-            s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-        }
-        if (ok && l == 0) {
+        if (kTwo) s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+        if (ok && h == 0) {
             qsm[y1 + r] = s1;
             if (kTwo) qsm[y2 + r] = s2;
         }
@@ -533,12 +710,14 @@ __device__ __noinline__ void f_matvec_cols(int W, int ld, int rows, int cols, in
             const double* Wp = qsm + W + cc;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int r = r0;
+#pragma unroll 1
             for (; r + 3 < r1; r += 4) {
                 s0 = fma(Wp[(r + 0) * ld], qsm[v + r + 0], s0);
                 s1 = fma(Wp[(r + 1) * ld], qsm[v + r + 1], s1);
                 s2 = fma(Wp[(r + 2) * ld], qsm[v + r + 2], s2);
                 s3 = fma(Wp[(r + 3) * ld], qsm[v + r + 3], s3);
             }
+#pragma unroll 1
             for (; r < r1; ++r) s0 = fma(Wp[r * ld], qsm[v + r], s0);
             qsm[(gidx ? p1 : p0) + cc] = (s0 + s1) + (s2 + s3);
         }
@@ -552,30 +731,29 @@ __device__ __noinline__ void f_matvec_cols(int W, int ld, int rows, int cols, in
     __syncthreads();
 }
 
-// || L x ||^2 partial sums (packed lower L in shared memory): 4 lanes per row, rows paired (r, n-1-r) for
-// balance, x cached in registers. Returns this thread's partial; sum over the block afterwards.
+// || L x ||^2 partial sums (packed lower L in shared memory): 4 lanes per row, rows paired (r, n-1-r) so that every
+// lane group streams n + 1 entries. Returns this thread's partial (lane l == 0 of a group); sum over the block after.
 __device__ __noinline__ double f_tri_norm2(int Lp, int n, int x) {
     QPB_SMEM;
     const int tid = threadIdx.x, q4 = tid >> 2, l = tid & 3;
-    constexpr int kMaxK = 32;                       // covers n <= 128; larger n falls back below
-    if (n > 4 * kMaxK) return tri_norm2_partial(qsm + Lp, n, qsm + x, tid, kNT);
-    double xr[kMaxK];
-#pragma unroll
-    for (int k = 0; k < kMaxK; ++k) xr[k] = (l + 4 * k < n) ? qsm[x + l + 4 * k] : 0.0;
     double acc = 0.0;
     const int npairs = (n + 1) >> 1;
-    for (int pi = q4; pi < npairs + ((64 - npairs % 64) % 64); pi += 64) {   // warp-uniform trip count
+    for (int pb = 0; pb < npairs; pb += kNT / 4) {           // warp-uniform trip count
+        const int pi = pb + q4;
         const bool act = pi < npairs;
         const int ra = act ? pi : 0, rb = n - 1 - ra;
         const double* La = qsm + Lp + (ra * (ra + 1)) / 2;
         const double* Lb = qsm + Lp + (rb * (rb + 1)) / 2;
         double sa = 0.0, sb = 0.0;
-#pragma unroll
-        for (int k = 0; k < kMaxK; ++k) {
-            const int c = l + 4 * k;
-            if (act && c <= ra) sa = fma(La[c], xr[k], sa);
-            if (act && c <= rb && rb != ra) sb = fma(Lb[c], xr[k], sb);
+        if (act) {
+#pragma unroll 2
+            for (int c = l; c <= ra; c += 4) sa = fma(La[c], qsm[x + c], sa);
+            if (rb != ra) {
+#pragma unroll 2
+                for (int c = l; c <= rb; c += 4) sb = fma(Lb[c], qsm[x + c], sb);
+            }
         }
+        __syncwarp();                                        // (the row loops above diverge)
         sa += __shfl_xor_sync(0xffffffffu, sa, 1); sb += __shfl_xor_sync(0xffffffffu, sb, 1);
         sa += __shfl_xor_sync(0xffffffffu, sa, 2); sb += __shfl_xor_sync(0xffffffffu, sb, 2);
         if (l == 0) acc = fma(sa, sa, fma(sb, sb, acc));

@@ -696,17 +696,16 @@ struct FCtx {
 };
 #define FV(i) (C.L.vec + (i) * C.L.vl)
 
-__device__ __forceinline__ void f_issue_K(const KDims& D, FCtx& C) {
+__device__ __noinline__ void f_issue_K_impl(int LS, const double* Kg, int bar_off, uint32_t bytes) {
     QPB_SMEM;
-    const int tid = threadIdx.x;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(qsm + C.L.bar);
-    if (tid < 32) {
-        fence_proxy_async();
-        const uint32_t bytes = (uint32_t)(D.msp * D.lds * 8);
-        if (tid == 0) mbar_expect_tx(bar + 1, bytes);
-        __syncwarp();
-        bulk_issue_warp(qsm + C.L.LS, C.Kg, bytes, bar + 1, tid);
-    }
+    uint64_t* bar = reinterpret_cast<uint64_t*>(qsm + bar_off);
+    fence_proxy_async();
+    mbar_expect_tx(bar + 1, bytes);
+    bulk_issue_thread(qsm + LS, Kg, bytes, bar + 1);
+}
+// Call with all threads AFTER a block barrier that retired every reader of the previous factor.
+__device__ __forceinline__ void f_issue_K(const KDims& D, FCtx& C) {
+    if (threadIdx.x == 0) f_issue_K_impl(C.L.LS, C.Kg, C.L.bar, (uint32_t)(D.msp * D.lds * 8));
     C.kpending = true;
 }
 __device__ __forceinline__ void f_wait_K(FCtx& C) {
@@ -737,12 +736,11 @@ __device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double*
     }
     build_tile_table(reinterpret_cast<uint16_t*>(qsm + C.L.tab), (D.msp - D.ep) >> 3, tid);
     __syncthreads();
-    if (tid < 32) {
+    if (tid == 0) {
         const uint32_t wb = (uint32_t)(D.ms * D.ldw * 8), lb = (uint32_t)(D.lp * 8);
-        if (tid == 0) mbar_expect_tx(bar, wb + lb);
-        __syncwarp();
-        bulk_issue_warp(qsm + C.L.W, Wg, wb, bar, tid);
-        bulk_issue_warp(qsm + C.L.Lp, Lg, lb, bar, tid);
+        mbar_expect_tx(bar, wb + lb);
+        bulk_issue_thread(qsm + C.L.W, Wg, wb, bar);
+        bulk_issue_thread(qsm + C.L.Lp, Lg, lb, bar);
     }
     f_issue_K(D, C);
     mbar_wait(bar, 0);
@@ -752,7 +750,8 @@ __device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double*
 }
 
 // factor_kkt + first half of solve_kkt: F_AUG = -h_full (pad entries 0), F_D = d  ->  F_W = -S^-1 h_full
-__device__ __forceinline__ void f_factor_and_solve(const KDims& D, FCtx& C) {
+// pform: rewrite the factor in product form (worth it when two more solves with the same factor follow)
+__device__ __forceinline__ void f_factor_and_solve(const KDims& D, FCtx& C, bool pform) {
     QPB_SMEM;
     const int tid = threadIdx.x;
     f_wait_K(C);
@@ -765,11 +764,171 @@ __device__ __forceinline__ void f_factor_and_solve(const KDims& D, FCtx& C) {
     }
     f_chol(C.L.LS, D.lds, D.msp, D.ep, FV(F_AUG), C.L.tab);
     QPB_TICK(32);   // (chol internals are 20..27)
-    f_trsv_bwd(C.L.LS, D.lds, D.msp, FV(F_AUG), FV(F_W));
+#if QPB_PFORM
+    if (pform) {
+        f_to_pform(C.L.LS, D.lds, D.msp);                      // T_k, P_ik: every later solve is chain-free
+        QPB_TICK(28);   // product-form conversion
+        f_ptrsv_bwd(C.L.LS, D.lds, D.msp, FV(F_AUG), FV(F_W));
+    } else
+#endif
+    {
+        f_trsv_bwd(C.L.LS, D.lds, D.msp, FV(F_AUG), FV(F_W));
+    }
     QPB_TICK(33);   // backward substitution
 }
 
 __device__ __forceinline__ double f_step_fix(double v) { return (isinf(v) && v > 0.0) ? 1.0 : v; }
+
+// ---- the "vector group": all O(m) step logic of one Newton iteration on warps 0..3 ---------------------------
+// The vectors of the reduced system have ms <= 224 entries: thread t < 128 owns entries t, t + 128. The four warps
+// sit on the four SM sub-partitions, reduce with shuffles + one 128-thread named barrier (no block-wide barrier,
+// no two-barrier shared-memory reduction per min / sum) and run dependent sweeps back to back; warps 4..7 wait at
+// the next __syncthreads. Scalars go through ctl[] (shared memory). fp64 divide / sqrt and the reductions are
+// shared subroutines: inlined, the three routines were 60 KB of SASS and ran at the speed of instruction fetch.
+#ifndef QPB_VECWARP
+#define QPB_VECWARP 1
+#endif
+constexpr int kVG = 128;
+enum { CTL_MU = 0, CTL_RESID, CTL_PRI, CTL_DUAL, CTL_ALPHA, CTL_COUNT };
+
+__device__ __noinline__ double f_div(double a, double b) { return a / b; }
+__device__ __noinline__ double f_sqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ double f_cand(double v, double dv) { return (dv > 0.0) ? INFINITY : f_div(-v, dv); }
+
+// reductions over the vector group; slot = 8 doubles of scratch, 16-byte aligned, distinct per call site
+__device__ __noinline__ double2 f_vg_sum2(double a, double b, int slot) {
+    QPB_SMEM;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) { qsm[slot + warp] = a; qsm[slot + 4 + warp] = b; }
+    named_bar_sync(2, kVG);
+    const double2 a0 = *reinterpret_cast<const double2*>(qsm + slot), a1 = *reinterpret_cast<const double2*>(qsm + slot + 2);
+    const double2 b0 = *reinterpret_cast<const double2*>(qsm + slot + 4), b1 = *reinterpret_cast<const double2*>(qsm + slot + 6);
+    return make_double2((a0.x + a0.y) + (a1.x + a1.y), (b0.x + b0.y) + (b1.x + b1.y));
+}
+__device__ __noinline__ double2 f_vg_min2(double a, double b, int slot) {
+    QPB_SMEM;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warp_min(a); b = warp_min(b);
+    if (lane == 0) { qsm[slot + warp] = a; qsm[slot + 4 + warp] = b; }
+    named_bar_sync(2, kVG);
+    const double2 a0 = *reinterpret_cast<const double2*>(qsm + slot), a1 = *reinterpret_cast<const double2*>(qsm + slot + 2);
+    const double2 b0 = *reinterpret_cast<const double2*>(qsm + slot + 4), b1 = *reinterpret_cast<const double2*>(qsm + slot + 6);
+    return make_double2(fmin(fmin(a0.x, a0.y), fmin(a1.x, a1.y)), fmin(fmin(b0.x, b0.y), fmin(b1.x, b1.y)));
+}
+
+// residuals (batch.py:94-107) + d = z/s and the affine right-hand side (batch.py:109,150).
+// in: rv = W x~, hW = W r~x, tri[0..7] = per-warp partial sums of |L r~x|^2.  out: rv = [ry; rz], d, aug, ctl[].
+// scr: 16 doubles of scratch.
+__device__ __noinline__ void f_vec_resid(int rv, int hb, int s, int v, int hW, int d, int aug, int tri, int ctl,
+                                         int scr, int ep, int ms, double dm) {
+    QPB_SMEM;
+    const int tid = threadIdx.x;
+    double a0 = 0.0, a1 = 0.0, a3 = 0.0;
+#pragma unroll 1
+    for (int i = tid; i < ms; i += kVG) {
+        const double si = (i >= ep) ? qsm[s + i] : 0.0;
+        const double r = qsm[rv + i] - qsm[hb + i] + si;
+        qsm[rv + i] = r;
+        if (i < ep) a0 = fma(r, r, a0);
+        else { a1 = fma(r, r, a1); a3 = fma(si, qsm[v + i], a3); }
+    }
+    double a2 = (tid < kNT / 32) ? qsm[tri + tid] : 0.0;
+    QPB_TICK(34);
+    const double2 r01 = f_vg_sum2(a0, a1, scr), r23 = f_vg_sum2(a2, a3, scr + 8);
+    a0 = r01.x; a1 = r01.y; a2 = r23.x; a3 = r23.y;
+    QPB_TICK(35);
+    const double mu = fabs(f_div(a3, dm));
+    const double pri = f_sqrt(a1) + f_sqrt(a0), dual = f_sqrt(a2);
+    if (tid == 0) {
+        qsm[ctl + CTL_MU] = mu; qsm[ctl + CTL_RESID] = pri + dual + dm * mu;
+        qsm[ctl + CTL_PRI] = pri; qsm[ctl + CTL_DUAL] = dual;
+    }
+    QPB_TICK(36);
+#pragma unroll 1
+    for (int i = tid; i < ms; i += kVG) {
+        double hfull = qsm[hW + i] - qsm[rv + i];
+        if (i >= ep) {
+            const double vi = qsm[v + i];
+            const double di = f_div(vi, qsm[s + i]);
+            qsm[d + i] = di;
+            hfull += f_div(vi, di);
+        }
+        qsm[aug + i] = -hfull;
+    }
+}
+
+// affine step length, sigma, corrector right-hand side (batch.py:160-181). in: w = [dy_aff; dz_aff].
+// out: dsa, ds (= corrector rs), t1 (= right-hand side of the corrector solve, all msp entries).
+__device__ __noinline__ void f_vec_affine(int w, int v, int s, int d, int dsa, int ds, int t1, int scr, int ep,
+                                          int ms, int msp, double mu) {
+    QPB_SMEM;
+    const int tid = threadIdx.x;
+    double mn0 = INFINITY, mn1 = INFINITY;
+#pragma unroll 1
+    for (int i = ep + tid; i < ms; i += kVG) {
+        const double dz = qsm[w + i], vi = qsm[v + i];
+        const double dsi = f_div(-vi - dz, qsm[d + i]);
+        qsm[dsa + i] = dsi;
+        mn0 = fmin(mn0, f_cand(vi, dz));
+        mn1 = fmin(mn1, f_cand(qsm[s + i], dsi));
+    }
+    QPB_TICK(41);
+    const double2 mn = f_vg_min2(mn0, mn1, scr);
+    QPB_TICK(43);
+    const double alpha = fmin(fmin(f_step_fix(mn.x), f_step_fix(mn.y)), 1.0);
+    double sm0 = 0.0, sm1 = 0.0;
+#pragma unroll 1
+    for (int i = ep + tid; i < ms; i += kVG) {
+        const double si = qsm[s + i], vi = qsm[v + i];
+        sm0 = fma(si + alpha * qsm[dsa + i], vi + alpha * qsm[w + i], sm0);
+        sm1 = fma(si, vi, sm1);
+    }
+    const double2 sm = f_vg_sum2(sm0, sm1, scr + 8);
+    const double sr = f_div(sm.x, sm.y);
+    const double musig = mu * (sr * sr * sr);
+    QPB_TICK(45);
+#pragma unroll 1
+    for (int i = tid; i < msp; i += kVG) {
+        double rhs = 0.0;
+        if (i >= ep && i < ms) {
+            const double rsc = f_div(-musig + qsm[dsa + i] * qsm[w + i], qsm[s + i]);
+            qsm[ds + i] = rsc;
+            rhs = -f_div(rsc, qsm[d + i]);
+        }
+        qsm[t1 + i] = rhs;
+    }
+}
+
+// combined direction, step length, update of [y; z] and s (batch.py:185-203). in: t1 = [dy_cor; dz_cor].
+// out: w = [dy; dz], ds, v += alpha dv, s += alpha ds, ctl[CTL_ALPHA] (x~ is updated by the caller after W^T dv).
+__device__ __noinline__ void f_vec_combine(int w, int t1, int v, int s, int d, int dsa, int ds, int ctl, int scr,
+                                           int ep, int ms) {
+    QPB_SMEM;
+    const int tid = threadIdx.x;
+    double mn0 = INFINITY, mn1 = INFINITY;
+#pragma unroll 1
+    for (int i = tid; i < ms; i += kVG) {
+        const double wci = qsm[t1 + i];
+        const double dv = qsm[w + i] + wci;
+        qsm[w + i] = dv;
+        if (i >= ep) {
+            const double dsc = f_div(-qsm[ds + i] - wci, qsm[d + i]);
+            const double dsi = qsm[dsa + i] + dsc;
+            qsm[ds + i] = dsi;
+            mn0 = fmin(mn0, f_cand(qsm[v + i], dv));
+            mn1 = fmin(mn1, f_cand(qsm[s + i], dsi));
+        }
+    }
+    const double2 mn = f_vg_min2(mn0, mn1, scr);
+    const double alpha = fmin(0.999 * fmin(f_step_fix(mn.x), f_step_fix(mn.y)), 1.0);
+    if (tid == 0) qsm[ctl + CTL_ALPHA] = alpha;
+#pragma unroll 1
+    for (int i = tid; i < ms; i += kVG) {
+        qsm[v + i] = fma(alpha, qsm[w + i], qsm[v + i]);
+        if (i >= ep) qsm[s + i] = fma(alpha, qsm[ds + i], qsm[s + i]);
+    }
+}
 }  // namespace fk
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -821,7 +980,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     __syncthreads();
     _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) qsm[aug + i] = -(qsm[hW + i] + qsm[hb + i]);
     __syncthreads();
-    f_factor_and_solve(D, C);
+    f_factor_and_solve(D, C, false);
     f_issue_K(D, C);
     f_matvec_cols(W, ldw, ms, n, w, t0, t1, xt, pt, -1.0, -1, -1.0);   // x~ = -p~ - W^T w
     {
@@ -846,6 +1005,82 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     double best = 0.0, ret_resid = 0.0;
     int nNot = 0, iters_run = 0;
     const double dm = (double)m;
+#if QPB_VECWARP
+    const int tri = C.L.red + 104, ctl = C.L.red + 112, vscr = C.L.red;   // (red[0..103] is reduction scratch)
+    for (int it = 0; it < maxIter; ++it) {
+        iters_run = it + 1;
+        // ---- residuals (batch.py:94-107)
+        QPB_TICK(3);
+        f_matvec_cols(W, ldw, ms, n, v, t0, t1, rxt, xt, 1.0, pt, 1.0);      // r~x = x~ + p~ + W^T [y;z]
+        QPB_TICK(4);
+#ifdef QPB_TIMING_REPEAT   // cold vs warm cost of idempotent phases (instruction-cache experiment)
+        f_matvec_cols(W, ldw, ms, n, v, t0, t1, rxt, xt, 1.0, pt, 1.0); QPB_TICK(61);
+        f_matvec_cols(W, ldw, ms, n, v, t0, t1, rxt, xt, 1.0, pt, 1.0); QPB_TICK(62);
+#endif
+        f_matvec_rows2(W, ldw, ms, n, xt, rxt, rv, hW);                      // W x~ , W r~x
+        QPB_TICK(5);
+#ifdef QPB_TIMING_REPEAT
+        __syncthreads();
+        f_matvec_rows2(W, ldw, ms, n, xt, rxt, rv, hW); __syncthreads(); QPB_TICK(77);
+        f_matvec_rows2(W, ldw, ms, n, xt, rxt, rv, hW); __syncthreads(); QPB_TICK(78);
+        { double z1 = f_tri_norm2(C.L.Lp, n, rxt); if (z1 == -1.0) qsm[0] = z1; } __syncthreads(); QPB_TICK(93);
+        { double z1 = f_tri_norm2(C.L.Lp, n, rxt); if (z1 == -1.0) qsm[0] = z1; } __syncthreads(); QPB_TICK(94);
+#endif
+        {
+            const double tp = warp_sum(f_tri_norm2(C.L.Lp, n, rxt));         // |L r~x|^2 = |Qx + p + G^T z + A^T y|^2
+            if ((tid & 31) == 0) qsm[tri + (tid >> 5)] = tp;
+        }
+        __syncthreads();
+        QPB_TICK(7);
+        if (tid < kVG) f_vec_resid(rv, hb, s, v, hW, d, aug, tri, ctl, vscr, ep, ms, dm);
+        __syncthreads();
+        QPB_TICK(6);
+        const double mu = qsm[ctl + CTL_MU], resid = qsm[ctl + CTL_RESID];
+        if (trace != nullptr && tid == 0) {                     // what verbose=1 prints (batch.py:115-117)
+            double* tr = trace + ((int64_t)qp * maxIter + it) * 4;
+            tr[0] = qsm[ctl + CTL_PRI]; tr[1] = qsm[ctl + CTL_DUAL]; tr[2] = mu; tr[3] = resid;
+        }
+        // ---- best-iterate tracking and exit tests (batch.py:118-143), per QP (see k_forward)
+        const bool improved = (it == 0) || (resid < best);
+        if (improved) { best = resid; nNot = 0; } else { ++nNot; }
+        if (improved || resid < best_tie * best) {
+            ret_resid = resid;
+            _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[FV(F_BXT) + i] = qsm[xt + i];
+            _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) { qsm[FV(F_BS) + i] = qsm[s + i]; qsm[FV(F_BV) + i] = qsm[v + i]; }
+        }
+        if ((nNot == notImprovedLim && best < stall_tol) || best < eps || mu > 1e32) break;
+        if (!(resid == resid) || isinf(resid)) break;
+        QPB_TICK(9);
+        // ---- factor_kkt with d = z/s and the affine right-hand side (batch.py:109-113,150): d, aug set by f_vec_resid
+        f_factor_and_solve(D, C, true);                               // w = [dy_aff; dz_aff]
+        QPB_TICK(10);
+        if (tid < kVG) f_vec_affine(w, v, s, d, dsa, ds, t1, vscr + 16, ep, ms, msp, mu);      // batch.py:160-181
+        __syncthreads();
+        QPB_TICK(11);
+#if QPB_PFORM
+        f_ptrsv_fwd(C.L.LS, D.lds, msp, t1, t0);
+        QPB_TICK(12);
+        f_ptrsv_bwd(C.L.LS, D.lds, msp, t0, t1);                 // t1 = [dy_cor; dz_cor]
+#else
+        f_trsv_fwd(C.L.LS, D.lds, msp, 0, msp, t1, t0);
+        QPB_TICK(12);
+        f_trsv_bwd(C.L.LS, D.lds, msp, t0, t1);                  // t1 = [dy_cor; dz_cor]
+#endif
+        QPB_TICK(13);
+        f_issue_K(D, C);                                         // next factor_kkt's K copy overlaps the rest
+        // ---- combined direction, step length, update (batch.py:185-203)
+        if (tid < kVG) f_vec_combine(w, t1, v, s, d, dsa, ds, ctl, vscr + 32, ep, ms);
+        __syncthreads();
+        QPB_TICK(14);
+        f_matvec_cols(W, ldw, ms, n, w, t0, t1, hW, rxt, -1.0, -1, -1.0);     // dx~ = -r~x - W^T dv  (in hW)
+        QPB_TICK(15);
+        {
+            const double alpha = qsm[ctl + CTL_ALPHA];
+            _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[xt + i] = fma(alpha, qsm[hW + i], qsm[xt + i]);
+        }
+        __syncthreads();
+    }
+#else
     for (int it = 0; it < maxIter; ++it) {
         iters_run = it + 1;
         // ---- residuals (batch.py:94-107)
@@ -895,7 +1130,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         }
         __syncthreads();
         QPB_TICK(9);
-        f_factor_and_solve(D, C);                               // w = [dy_aff; dz_aff]
+        f_factor_and_solve(D, C, true);                               // w = [dy_aff; dz_aff]
         QPB_TICK(10);
         // ---- affine step length and sigma (batch.py:160-168)
         double mn[2] = {INFINITY, INFINITY};
@@ -930,9 +1165,15 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
             __syncthreads();
         }
         QPB_TICK(11);
+#if QPB_PFORM
+        f_ptrsv_fwd(C.L.LS, D.lds, msp, t1, t0);
+        QPB_TICK(12);
+        f_ptrsv_bwd(C.L.LS, D.lds, msp, t0, t1);                 // t1 = [dy_cor; dz_cor]
+#else
         f_trsv_fwd(C.L.LS, D.lds, msp, 0, msp, t1, t0);
         QPB_TICK(12);
         f_trsv_bwd(C.L.LS, D.lds, msp, t0, t1);                  // t1 = [dy_cor; dz_cor]
+#endif
         QPB_TICK(13);
         f_issue_K(D, C);                                         // next factor_kkt's K copy overlaps the rest
         // ---- combined direction, step length, update (batch.py:185-203)
@@ -964,6 +1205,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         }
         __syncthreads();
     }
+#endif
 
     // ---- outputs: x = L^-T x~_best, y, z, s of the returned iterate (batch.py:205-207)
     __syncthreads();
@@ -1031,7 +1273,7 @@ k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ 
     __syncthreads();
     _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) qsm[aug + i] = -(qsm[c2 + i] + qsm[hW + i]);
     __syncthreads();
-    f_factor_and_solve(D, C);                                   // w = [dy; dz]
+    f_factor_and_solve(D, C, false);                                   // w = [dy; dz]
     f_matvec_cols(W, ldw, ms, n, w, t0, t1, dxt, t, -1.0, -1, -1.0);
     f_unwhiten(C.L.Lp, n, FV(F_DINVL), dxt, dxo);               // dx = L^-T dx~
     _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) dx_out[(int64_t)qp * n + i] = qsm[dxo + i];
