@@ -196,7 +196,7 @@ def run_b200(args, rank, world, local_rank):
     # (and as in the e2e leg below) consecutive steps alternate between INFLIGHT CUDA streams: the next batch's
     # CTAs take over the SMs the previous batch has already released. Every step is still one complete
     # forward + backward over its own batch; the single-stream figure is reported next to it (config.serial_*).
-    inflight = max(1, env_int("QPB_BENCH_INFLIGHT", 2))
+    inflight = max(1, env_int("QPB_BENCH_INFLIGHT", 3))
     vstreams = [torch.cuda.Stream(device=dev) for _ in range(inflight)]
 
     def timed_window(nsteps, first, streams):
@@ -249,7 +249,7 @@ def run_b200(args, rank, world, local_rank):
     # (~0.6 ms), D2H (~0.5 ms) in sequence on its stream, so two streams leave the PCIe link idle a third of the
     # time; with three the link (full duplex, ~33 GB/s each way measured) or the SMs are the limit. Every step
     # still moves all of its own bytes.
-    NS = max(1, env_int("QPB_BENCH_E2E_INFLIGHT", 3))
+    NS = max(1, env_int("QPB_BENCH_E2E_INFLIGHT", 4))
     hb = make_batches(dev, 1000 * rank, NS, pinned_host=True)
     host_out = [{k: torch.empty(s, dtype=torch.float64).pin_memory()
                  for k, s in (("z", (B, n)), ("dQ", (B, n, n)), ("dp", (B, n)), ("dG", (B, m, n)), ("dh", (B, m)))}

@@ -78,7 +78,38 @@ __device__ __forceinline__ double f_rsqrt(double x) {
 }
 
 // In-register factorization of an 8x8 block (lower triangle in Lk): on exit strictly lower = L, diagonal = 1/L_cc.
+// Columns are eliminated in PAIRS: with a = A_cc, b = A_c+1,c, e = A_c+1,c+1 the second pivot is det / a,
+// det = a e - b^2, so 1/L_c+1,c+1 = rsqrt(det) * sqrt(a) and the two rsqrt (the longest link of the chain: MUFU +
+// 4 dependent fp64 ops) run side by side: ~100 cycles per pair instead of 2 x 72.
+#ifndef QPB_CHAIN_V2
+#define QPB_CHAIN_V2 0   // measured: no gain on B200 (530.7 vs 531.0 us forward), kept for reference
+#endif
 __device__ __forceinline__ void f_factor8_regs(double (&Lk)[36]) {
+#if QPB_CHAIN_V2
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+        const double a = Lk[QPB_LIDX(c, c)], b = Lk[QPB_LIDX(c + 1, c)], e = Lk[QPB_LIDX(c + 1, c + 1)];
+        const double r1 = f_rsqrt(a);
+        const double det = fma(a, e, -(b * b));
+        const double r2 = f_rsqrt(det) * (a * r1);
+        const double l10 = b * r1;
+        Lk[QPB_LIDX(c, c)] = r1;
+        Lk[QPB_LIDX(c + 1, c)] = l10;
+        Lk[QPB_LIDX(c + 1, c + 1)] = r2;
+#pragma unroll
+        for (int r = c + 2; r < 8; ++r) {
+            const double l1 = Lk[QPB_LIDX(r, c)] * r1;
+            Lk[QPB_LIDX(r, c)] = l1;
+            Lk[QPB_LIDX(r, c + 1)] = fma(-l1, l10, Lk[QPB_LIDX(r, c + 1)]) * r2;
+        }
+#pragma unroll
+        for (int r = c + 2; r < 8; ++r)
+#pragma unroll
+            for (int cc = c + 2; cc <= r; ++cc)
+                Lk[QPB_LIDX(r, cc)] = fma(-Lk[QPB_LIDX(r, c + 1)], Lk[QPB_LIDX(cc, c + 1)],
+                                          fma(-Lk[QPB_LIDX(r, c)], Lk[QPB_LIDX(cc, c)], Lk[QPB_LIDX(r, cc)]));
+    }
+#else
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const double ri = f_rsqrt(Lk[QPB_LIDX(c, c)]);
@@ -91,6 +122,23 @@ __device__ __forceinline__ void f_factor8_regs(double (&Lk)[36]) {
             for (int cc = c + 1; cc <= r; ++cc)
                 Lk[QPB_LIDX(r, cc)] = fma(-Lk[QPB_LIDX(r, c)], Lk[QPB_LIDX(cc, c)], Lk[QPB_LIDX(r, cc)]);
     }
+#endif
+}
+// Row-scaled copy of a factored block, Ls[r][c] = L[r][c] / L[r][r] (c < r): with it the substitution
+// a <- a * L_kk^-T has ONE dependent FMA per entry instead of a multiply and an FMA (72 vs 140 cycles for 8).
+__device__ __forceinline__ void f_scale_rows8(const double (&Lk)[36], double (&Ls)[28]) {
+#pragma unroll
+    for (int r = 1; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < r; ++c) Ls[QPB_LIDX(r - 1, c)] = Lk[QPB_LIDX(r, c)] * Lk[QPB_LIDX(r, r)];
+}
+__device__ __forceinline__ void f_row_solve8_scaled(double (&a)[8], const double (&Lk)[36], const double (&Ls)[28]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] *= Lk[QPB_LIDX(c, c)];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; ++c2) a[c2] = fma(-a[c], Ls[QPB_LIDX(c2 - 1, c)], a[c2]);
 }
 __device__ __forceinline__ void f_store_lower8(double* Mb, int ld, const double (&Lk)[36]) {
 #pragma unroll
@@ -181,6 +229,9 @@ __device__ __noinline__ void f_chol_chain(int A, int ld, int n, int c0) {
     const int nts = (n - c0) >> 3;
     double* M = qsm + A;
     double Lk[36];                                           // the current diagonal block stays in registers
+#if QPB_CHAIN_V2
+    double Ls[28];                                           // its row-scaled copy (for s_k)
+#endif
     // k = -1 is the prologue step (F_0 only): ONE instance of the unrolled 8x8 factorization in the code.
     for (int k = -1; k < nts; ++k) {
         const int k0 = c0 + 8 * k;
@@ -190,7 +241,11 @@ __device__ __noinline__ void f_chol_chain(int A, int ld, int n, int c0) {
                 double a[8];
                 double* rowp = M + (k0 + 8 + lane) * ld + k0;
                 f_ld8(rowp, a);
+#if QPB_CHAIN_V2
+                f_row_solve8_scaled(a, Lk, Ls);
+#else
                 f_row_solve8(a, Lk);
+#endif
                 f_st8(rowp, a);
             }
             __syncwarp();
@@ -212,6 +267,9 @@ __device__ __noinline__ void f_chol_chain(int A, int ld, int n, int c0) {
             __syncwarp();                                                             // all lanes have read the tile
             f_factor8_regs(Lk);                                                       // F_{k+1}
             if (lane == 0) f_store_lower8(M + (k0 + 8) * ld + k0 + 8, ld, Lk);
+#if QPB_CHAIN_V2
+            f_scale_rows8(Lk, Ls);
+#endif
             if (k >= 0) QPB_TICK(80 + k);   // F_{k+1}, per step
         }
         QPB_TICK(26);
@@ -405,7 +463,7 @@ __device__ __noinline__ void f_trsv_bwd(int A, int ld, int n, int u, int w) {
 // dependent, redone by every thread) is gone and y_k is off the critical path. Costs one pass over the factor
 // (36 FMAs per row and block) per factorization; pays for itself with the three solves that follow.
 #ifndef QPB_PFORM
-#define QPB_PFORM 1
+#define QPB_PFORM 0      // measured (profiles/r1_experiments.md): the conversion pass costs what the chain-free solves save
 #endif
 
 // Upper triangle incl. diagonal of the 8x8 tile at Mb: T[QPB_LIDX(j, c)] = Mb[c][j], j >= c  (= T_k[j][c]).
@@ -461,6 +519,7 @@ __device__ __noinline__ void f_to_pform(int A, int ld, int n) {
     {
         const int g = lane >> 2, q = lane & 3;
         int item = 0;
+        const double zero = (double)(n >> 20);               // 0.0 the compiler cannot fold: the accumulator is a register, not RZ
 #pragma unroll 1
         for (int k = 0; k + 1 < nts; ++k) {
             const int k0 = 8 * k;
@@ -472,13 +531,15 @@ __device__ __noinline__ void f_to_pform(int A, int ld, int n) {
                 if ((item & 7) != warp) continue;
                 double* rowp = M + (8 * ti + g) * ld + k0;
                 const double a0 = rowp[q], a1 = rowp[q + 4];
-                double d0 = 0.0, d1 = 0.0;
+                double d0 = zero, d1 = zero;                                 // (a register, not RZ: see `zero` above)
                 dmma884(d0, d1, a0, b0);
                 dmma884(d0, d1, a1, b1);
                 *reinterpret_cast<double2*>(rowp + 2 * q) = make_double2(d0, d1);
             }
+            if (k == 0) QPB_TICK(29);   // first block column (12 of the 78 tiles)
         }
     }
+    QPB_TICK(25);   // P conversion, before its barrier
     __syncthreads();
 }
 
@@ -512,6 +573,7 @@ __device__ __noinline__ void f_ptrsv_fwd(int A, int ld, int n, int b, int u) {
         }
         __syncthreads();
     }
+    QPB_TICK(27);   // ptrsv_fwd sweep
     if (tid < n) {                                           // y = blockdiag(T_k) b: T_k[r][c] = tile[c][r], c <= r
         const int k0 = tid & ~7, r = tid & 7;
         double y[8], t[8];

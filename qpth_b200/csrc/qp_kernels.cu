@@ -786,7 +786,7 @@ __device__ __forceinline__ double f_step_fix(double v) { return (isinf(v) && v >
 // the next __syncthreads. Scalars go through ctl[] (shared memory). fp64 divide / sqrt and the reductions are
 // shared subroutines: inlined, the three routines were 60 KB of SASS and ran at the speed of instruction fetch.
 #ifndef QPB_VECWARP
-#define QPB_VECWARP 1
+#define QPB_VECWARP 0    // measured: 570 vs 531 us forward (profiles/r1_experiments.md); the inline block-wide sweeps stay
 #endif
 constexpr int kVG = 128;
 enum { CTL_MU = 0, CTL_RESID, CTL_PRI, CTL_DUAL, CTL_ALPHA, CTL_COUNT };
@@ -795,33 +795,63 @@ __device__ __noinline__ double f_div(double a, double b) { return a / b; }
 __device__ __noinline__ double f_sqrt(double a) { return sqrt(a); }
 __device__ __forceinline__ double f_cand(double v, double dv) { return (dv > 0.0) ? INFINITY : f_div(-v, dv); }
 
-// reductions over the vector group; slot = 8 doubles of scratch, 16-byte aligned, distinct per call site
-__device__ __noinline__ double2 f_vg_sum2(double a, double b, int slot) {
+// reductions over the vector group. Two implementations:
+//  QPB_VG_SMEM = 0: shuffles inside each warp, 8 doubles at `slot` to combine the four warps;
+//  QPB_VG_SMEM = 1: no shuffles - every thread parks its partials in `buf` (2 x 128 + 16 doubles: the dead
+//                   AUG/T0/T1 vector slots), 16 threads add 16 entries each, everybody adds the 8 partial sums.
+#ifndef QPB_VG_SMEM
+#define QPB_VG_SMEM 0
+#endif
+template <bool kMin>
+__device__ __forceinline__ double2 f_vg_red2_impl(double a, double b, int slot, int buf) {
     QPB_SMEM;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    a = warp_sum(a); b = warp_sum(b);
+    const int tid = threadIdx.x;
+#if QPB_VG_SMEM
+  if (buf >= 0) {
+    qsm[buf + tid] = a; qsm[buf + kVG + tid] = b;
+    named_bar_sync(2, kVG);
+    if (tid < 16) {
+        const double* src = qsm + buf + (tid >> 3) * kVG + (tid & 7);
+        double x0 = src[0], x1 = src[8];
+#pragma unroll
+        for (int j = 2; j < 16; j += 2) {
+            x0 = kMin ? fmin(x0, src[8 * j]) : x0 + src[8 * j];
+            x1 = kMin ? fmin(x1, src[8 * j + 8]) : x1 + src[8 * j + 8];
+        }
+        qsm[buf + 2 * kVG + tid] = kMin ? fmin(x0, x1) : x0 + x1;
+    }
+    named_bar_sync(2, kVG);
+    const double2 p0 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG), p1 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 2),
+                  p2 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 4), p3 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 6),
+                  q0 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 8), q1 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 10),
+                  q2 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 12), q3 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 14);
+    named_bar_sync(2, kVG);                                  // buf may be reused by the next reduction right away
+    if (kMin) return make_double2(fmin(fmin(fmin(p0.x, p0.y), fmin(p1.x, p1.y)), fmin(fmin(p2.x, p2.y), fmin(p3.x, p3.y))),
+                                  fmin(fmin(fmin(q0.x, q0.y), fmin(q1.x, q1.y)), fmin(fmin(q2.x, q2.y), fmin(q3.x, q3.y))));
+    return make_double2(((p0.x + p0.y) + (p1.x + p1.y)) + ((p2.x + p2.y) + (p3.x + p3.y)),
+                        ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y)));
+  }
+#endif
+    const int lane = tid & 31, warp = tid >> 5;
+    QPB_TICK(18);   // (entry: whatever preceded the call)
+    a = kMin ? warp_min(a) : warp_sum(a); b = kMin ? warp_min(b) : warp_sum(b);
+    QPB_TICK(19);   // two warp reductions
     if (lane == 0) { qsm[slot + warp] = a; qsm[slot + 4 + warp] = b; }
     named_bar_sync(2, kVG);
+    QPB_TICK(22);   // named barrier (128 threads)
     const double2 a0 = *reinterpret_cast<const double2*>(qsm + slot), a1 = *reinterpret_cast<const double2*>(qsm + slot + 2);
     const double2 b0 = *reinterpret_cast<const double2*>(qsm + slot + 4), b1 = *reinterpret_cast<const double2*>(qsm + slot + 6);
+    if (kMin) return make_double2(fmin(fmin(a0.x, a0.y), fmin(a1.x, a1.y)), fmin(fmin(b0.x, b0.y), fmin(b1.x, b1.y)));
     return make_double2((a0.x + a0.y) + (a1.x + a1.y), (b0.x + b0.y) + (b1.x + b1.y));
 }
-__device__ __noinline__ double2 f_vg_min2(double a, double b, int slot) {
-    QPB_SMEM;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    a = warp_min(a); b = warp_min(b);
-    if (lane == 0) { qsm[slot + warp] = a; qsm[slot + 4 + warp] = b; }
-    named_bar_sync(2, kVG);
-    const double2 a0 = *reinterpret_cast<const double2*>(qsm + slot), a1 = *reinterpret_cast<const double2*>(qsm + slot + 2);
-    const double2 b0 = *reinterpret_cast<const double2*>(qsm + slot + 4), b1 = *reinterpret_cast<const double2*>(qsm + slot + 6);
-    return make_double2(fmin(fmin(a0.x, a0.y), fmin(a1.x, a1.y)), fmin(fmin(b0.x, b0.y), fmin(b1.x, b1.y)));
-}
+__device__ __noinline__ double2 f_vg_sum2(double a, double b, int slot, int buf) { return f_vg_red2_impl<false>(a, b, slot, buf); }
+__device__ __noinline__ double2 f_vg_min2(double a, double b, int slot, int buf) { return f_vg_red2_impl<true>(a, b, slot, buf); }
 
 // residuals (batch.py:94-107) + d = z/s and the affine right-hand side (batch.py:109,150).
 // in: rv = W x~, hW = W r~x, tri[0..7] = per-warp partial sums of |L r~x|^2.  out: rv = [ry; rz], d, aug, ctl[].
 // scr: 16 doubles of scratch.
 __device__ __noinline__ void f_vec_resid(int rv, int hb, int s, int v, int hW, int d, int aug, int tri, int ctl,
-                                         int scr, int ep, int ms, double dm) {
+                                         int scr, int buf, int ep, int ms, double dm) {
     QPB_SMEM;
     const int tid = threadIdx.x;
     double a0 = 0.0, a1 = 0.0, a3 = 0.0;
@@ -835,10 +865,11 @@ __device__ __noinline__ void f_vec_resid(int rv, int hb, int s, int v, int hW, i
     }
     double a2 = (tid < kNT / 32) ? qsm[tri + tid] : 0.0;
     QPB_TICK(34);
-    const double2 r01 = f_vg_sum2(a0, a1, scr), r23 = f_vg_sum2(a2, a3, scr + 8);
+    const double2 r01 = f_vg_sum2(a0, a1, scr, buf), r23 = f_vg_sum2(a2, a3, scr + 8, buf);
     a0 = r01.x; a1 = r01.y; a2 = r23.x; a3 = r23.y;
     QPB_TICK(35);
     const double mu = fabs(f_div(a3, dm));
+    QPB_TICK(23);   // one f_div call
     const double pri = f_sqrt(a1) + f_sqrt(a0), dual = f_sqrt(a2);
     if (tid == 0) {
         qsm[ctl + CTL_MU] = mu; qsm[ctl + CTL_RESID] = pri + dual + dm * mu;
@@ -860,7 +891,7 @@ __device__ __noinline__ void f_vec_resid(int rv, int hb, int s, int v, int hW, i
 
 // affine step length, sigma, corrector right-hand side (batch.py:160-181). in: w = [dy_aff; dz_aff].
 // out: dsa, ds (= corrector rs), t1 (= right-hand side of the corrector solve, all msp entries).
-__device__ __noinline__ void f_vec_affine(int w, int v, int s, int d, int dsa, int ds, int t1, int scr, int ep,
+__device__ __noinline__ void f_vec_affine(int w, int v, int s, int d, int dsa, int ds, int t1, int scr, int buf, int ep,
                                           int ms, int msp, double mu) {
     QPB_SMEM;
     const int tid = threadIdx.x;
@@ -874,7 +905,7 @@ __device__ __noinline__ void f_vec_affine(int w, int v, int s, int d, int dsa, i
         mn1 = fmin(mn1, f_cand(qsm[s + i], dsi));
     }
     QPB_TICK(41);
-    const double2 mn = f_vg_min2(mn0, mn1, scr);
+    const double2 mn = f_vg_min2(mn0, mn1, scr, buf);
     QPB_TICK(43);
     const double alpha = fmin(fmin(f_step_fix(mn.x), f_step_fix(mn.y)), 1.0);
     double sm0 = 0.0, sm1 = 0.0;
@@ -884,7 +915,7 @@ __device__ __noinline__ void f_vec_affine(int w, int v, int s, int d, int dsa, i
         sm0 = fma(si + alpha * qsm[dsa + i], vi + alpha * qsm[w + i], sm0);
         sm1 = fma(si, vi, sm1);
     }
-    const double2 sm = f_vg_sum2(sm0, sm1, scr + 8);
+    const double2 sm = f_vg_sum2(sm0, sm1, scr + 8, buf);
     const double sr = f_div(sm.x, sm.y);
     const double musig = mu * (sr * sr * sr);
     QPB_TICK(45);
@@ -903,7 +934,7 @@ __device__ __noinline__ void f_vec_affine(int w, int v, int s, int d, int dsa, i
 // combined direction, step length, update of [y; z] and s (batch.py:185-203). in: t1 = [dy_cor; dz_cor].
 // out: w = [dy; dz], ds, v += alpha dv, s += alpha ds, ctl[CTL_ALPHA] (x~ is updated by the caller after W^T dv).
 __device__ __noinline__ void f_vec_combine(int w, int t1, int v, int s, int d, int dsa, int ds, int ctl, int scr,
-                                           int ep, int ms) {
+                                           int buf, int ep, int ms) {
     QPB_SMEM;
     const int tid = threadIdx.x;
     double mn0 = INFINITY, mn1 = INFINITY;
@@ -920,7 +951,7 @@ __device__ __noinline__ void f_vec_combine(int w, int t1, int v, int s, int d, i
             mn1 = fmin(mn1, f_cand(qsm[s + i], dsi));
         }
     }
-    const double2 mn = f_vg_min2(mn0, mn1, scr);
+    const double2 mn = f_vg_min2(mn0, mn1, scr, buf);
     const double alpha = fmin(0.999 * fmin(f_step_fix(mn.x), f_step_fix(mn.y)), 1.0);
     if (tid == 0) qsm[ctl + CTL_ALPHA] = alpha;
 #pragma unroll 1
@@ -1007,6 +1038,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     const double dm = (double)m;
 #if QPB_VECWARP
     const int tri = C.L.red + 104, ctl = C.L.red + 112, vscr = C.L.red;   // (red[0..103] is reduction scratch)
+    const int vbuf = (3 * C.L.vl >= 2 * kVG + 16) ? aug : -1;   // AUG|T0|T1 (contiguous, dead inside the vector-group sweeps)
     for (int it = 0; it < maxIter; ++it) {
         iters_run = it + 1;
         // ---- residuals (batch.py:94-107)
@@ -1019,6 +1051,29 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
 #endif
         f_matvec_rows2(W, ldw, ms, n, xt, rxt, rv, hW);                      // W x~ , W r~x
         QPB_TICK(5);
+#ifdef QPB_TIMING_PROBES   // cost of warp-collective instructions in this kernel's context (slots 61-63, 77-79)
+        {
+            __syncthreads();
+            QPB_TICK(60);
+            double pv = qsm[xt + (tid & 63)], pw = qsm[rxt + (tid & 63)];
+            pv = warp_sum(pv); pw = warp_sum(pw); pv = warp_sum(pv); pw = warp_sum(pw);   // 4 warp sums, all 8 warps
+            QPB_TICK(61);
+            if (tid < 128) { pv = warp_sum(pv); pw = warp_sum(pw); pv = warp_sum(pv); pw = warp_sum(pw); }   // warps 0..3 only
+            QPB_TICK(62);
+            if (tid < 128) { pv = warp_min(pv); pw = warp_min(pw); pv = warp_min(pv); pw = warp_min(pw); }
+            QPB_TICK(63);
+            double c0 = pv, c1 = pw;
+            for (int r = 0; r < 8; ++r) { dmma884(c0, c1, pv, pw); dmma884(c0, c1, pw, pv); }            // 16 dependent DMMAs, all warps
+            QPB_TICK(77);
+            if (tid < 32) for (int r = 0; r < 8; ++r) { dmma884(c0, c1, pv, pw); dmma884(c0, c1, pw, pv); } // warp 0 alone
+            QPB_TICK(78);
+            for (int r = 0; r < 16; ++r) { c0 = fma(c0, pv, pw); c1 = fma(c1, pw, pv); }                 // 16 dependent DFMA pairs
+            QPB_TICK(79);
+            if (c0 + c1 == 1.2345e301) qsm[t0] = c0;                                                      // keep the results alive
+            __syncthreads();
+            QPB_TICK(93);
+        }
+#endif
 #ifdef QPB_TIMING_REPEAT
         __syncthreads();
         f_matvec_rows2(W, ldw, ms, n, xt, rxt, rv, hW); __syncthreads(); QPB_TICK(77);
@@ -1032,7 +1087,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         }
         __syncthreads();
         QPB_TICK(7);
-        if (tid < kVG) f_vec_resid(rv, hb, s, v, hW, d, aug, tri, ctl, vscr, ep, ms, dm);
+        if (tid < kVG) f_vec_resid(rv, hb, s, v, hW, d, aug, tri, ctl, vscr, vbuf, ep, ms, dm);
         __syncthreads();
         QPB_TICK(6);
         const double mu = qsm[ctl + CTL_MU], resid = qsm[ctl + CTL_RESID];
@@ -1054,7 +1109,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         // ---- factor_kkt with d = z/s and the affine right-hand side (batch.py:109-113,150): d, aug set by f_vec_resid
         f_factor_and_solve(D, C, true);                               // w = [dy_aff; dz_aff]
         QPB_TICK(10);
-        if (tid < kVG) f_vec_affine(w, v, s, d, dsa, ds, t1, vscr + 16, ep, ms, msp, mu);      // batch.py:160-181
+        if (tid < kVG) f_vec_affine(w, v, s, d, dsa, ds, t1, vscr + 16, vbuf, ep, ms, msp, mu);      // batch.py:160-181
         __syncthreads();
         QPB_TICK(11);
 #if QPB_PFORM
@@ -1069,7 +1124,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         QPB_TICK(13);
         f_issue_K(D, C);                                         // next factor_kkt's K copy overlaps the rest
         // ---- combined direction, step length, update (batch.py:185-203)
-        if (tid < kVG) f_vec_combine(w, t1, v, s, d, dsa, ds, ctl, vscr + 32, ep, ms);
+        if (tid < kVG) f_vec_combine(w, t1, v, s, d, dsa, ds, ctl, vscr + 32, vbuf, ep, ms);
         __syncthreads();
         QPB_TICK(14);
         f_matvec_cols(W, ldw, ms, n, w, t0, t1, hW, rxt, -1.0, -1, -1.0);     // dx~ = -r~x - W^T dv  (in hW)
