@@ -378,7 +378,7 @@ def run_b200(args, rank, world, local_rank):
                      "note": "latency/fp64-bound path (SURVEY 8d): HBM fraction is small by construction",
                      "fp64": {"achieved_tflops": flops / (k_ms * 1e-3) / 1e12, "peak_tflops_measured": fp64_peak,
                               "frac": flops / (k_ms * 1e-3) / 1e12 / fp64_peak}},
-        "cpu_baseline": cpu_baseline(sample_reps=3),
+        "cpu_baseline": cpu_baseline(sample_reps=3) if world == 1 else None,   # timed at N=1 only (task statement)
     }
     return line
 
