@@ -13,7 +13,9 @@ Differences from the reference, all documented in DESIGN.md:
   * arithmetic is fp64 on the device whatever the input dtype (fp32 inputs are
     promoted and the results cast back);
   * CPU tensors are accepted: they are copied to the current CUDA device,
-    solved there, and the results returned on the CPU.
+    solved there, and the results returned on the CPU;
+  * `solver=QPSolvers.CVXPY` (qp.py:97-120) needs the `cvxpy` package for its forward; its backward, and the
+    stand-alone `QPSolutionFunction` for solutions produced by any other solver, live in `solution.py`.
 """
 import ctypes
 from enum import Enum
@@ -191,9 +193,20 @@ def solve_backward(st, dl_dzhat, mean_flags, want):
 def QPFunction(eps=1e-12, verbose=0, notImprovedLim=3, maxIter=20, solver=QPSolvers.PDIPM_BATCHED,
                check_Q_spd=True):
     """Factory with the reference's signature (`qpth/qp.py:18-20`); returns `Function.apply`."""
+    if solver == QPSolvers.CVXPY:
+        # qp.py:97-120,142-143: per-sample CVXPY solve on the CPU, then pre_factor_kkt + the same backward.
+        from .solution import QPSolutionFunction, cvxpy_forward
+
+        def apply_cvxpy(Q_, p_, G_, h_, A_, b_):
+            nBatch = extract_nBatch(Q_, p_, G_, h_, A_, b_)
+            Q, p, G, h, A, b = (expandParam(X, nBatch, nd)[0]
+                                for X, nd in ((Q_, 3), (p_, 2), (G_, 3), (h_, 2), (A_, 3), (b_, 2)))
+            zhats, nus, lams, slacks = cvxpy_forward(Q, p, G, h, A, b)
+            return QPSolutionFunction(check_Q_spd)(Q_, p_, G_, h_, A_, b_, zhats, lams, slacks, nus)
+
+        return apply_cvxpy
     if solver != QPSolvers.PDIPM_BATCHED:
-        raise NotImplementedError("qpth_b200 implements QPSolvers.PDIPM_BATCHED only "
-                                  "(the CVXPY branch of qp.py:97-120 is out of scope)")
+        assert False                                     # qp.py:121-122
 
     _last = [None]
 
