@@ -111,7 +111,12 @@ def QPSolutionFunction(check_Q_spd=True):
                      for X, g in zip((Q, p, G, h, A, b), outs)]
             return tuple(grads) + (None, None, None, None)
 
-    return QPSolutionFn.apply
+    def apply(Q_, p_, G_, h_, A_, b_, zhat, lams, slacks, nus):
+        # the solution is a constant of this node: detach it, or autograd would walk back into whatever produced it
+        sol = [x.detach() if torch.is_tensor(x) else x for x in (zhat, lams, slacks, nus)]
+        return QPSolutionFn.apply(Q_, p_, G_, h_, A_, b_, *sol)
+
+    return apply
 
 
 def cvxpy_forward(Q, p, G, h, A, b):
