@@ -236,3 +236,36 @@ def test_host_buffer_entry_point():
     assert rel_rows(z, ref["zhat"]).max() <= ZTOL
     for g, r in zip((dQ, dp, dG, dh, dA, db), ref["grads"]):
         assert rel_rows(g, r, floor=1e-4).max() <= GTOL
+
+
+def test_concurrent_streams_match_serial():
+    """Several steps in flight on different CUDA streams (what bench.py and a serving loop do) must give exactly
+    the results of the same calls issued one after the other: the library keeps no per-call state on the device."""
+    from qpth_b200 import QPFunction
+    f = QPFunction(verbose=-1, check_Q_spd=False)
+    e = torch.Tensor().to(DEV).double()
+    probs = [random_qp_batch(32, 40, 30, 0, seed=100 + i) for i in range(4)]
+    ts = [{k: torch.tensor(pr[k], dtype=torch.float64, device=DEV, requires_grad=True) for k in ("Q", "p", "G", "h")}
+          for pr in probs]
+    dls = [torch.tensor(pr["dl"], dtype=torch.float64, device=DEV) for pr in probs]
+
+    def step(t, dl):
+        for v in t.values():
+            v.grad = None
+        z = f(t["Q"], t["p"], t["G"], t["h"], e, e)
+        z.backward(dl)
+        return z.detach().clone(), [t[k].grad.clone() for k in ("Q", "p", "G", "h")]
+
+    serial = [step(t, dl) for t, dl in zip(ts, dls)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in ts]
+    conc = []
+    for s_, t, dl in zip(streams, ts, dls):
+        s_.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s_):
+            conc.append(step(t, dl))
+    torch.cuda.synchronize()
+    for (z0, g0), (z1, g1) in zip(serial, conc):
+        assert torch.equal(z0, z1)
+        for a, b in zip(g0, g1):
+            assert torch.equal(a, b)
