@@ -1,42 +1,60 @@
-"""Shape / broadcast helpers with the reference's names and behaviour (`qpth/util.py`)."""
+"""Shape / broadcast helpers with the names and behaviour of the reference's `qpth/util.py`.
+
+Only `expandParam` / `extract_nBatch` are on the hot path (they define how un-batched parameters broadcast, rows a3 of
+SURVEY.md section 8); the rest is kept so that `from qpth.util import ...` keeps working after
+`qpth_b200.install_as_qpth()`.
+"""
+import numpy as np
 import torch
 
-
-def bger(x, y):
-    """Batched outer product (util.py:18-19)."""
-    return x.unsqueeze(2) * y.unsqueeze(1)
-
-
-def get_sizes(G, A=None):
-    """(nineq, nz, neq, nBatch) (util.py:22-33)."""
-    if G.dim() == 2:
-        nineq, nz = G.size()
-        nBatch = 1
-    elif G.dim() == 3:
-        nBatch, nineq, nz = G.size()
-    else:
-        raise RuntimeError("Unexpected number of dimensions.")
-    neq = None
-    if A is not None:
-        neq = A.size(1) if A.nelement() > 0 else 0
-    return nineq, nz, neq, nBatch
-
-
-def expandParam(X, nBatch, nDim):
-    """Un-batched -> stride-0 batch view and a flag saying so (util.py:44-50)."""
-    if X.ndimension() in (0, nDim) or X.nelement() == 0:
-        return X, False
-    elif X.ndimension() == nDim - 1:
-        return X.unsqueeze(0).expand(*([nBatch] + list(X.size()))), True
-    else:
-        raise RuntimeError("Unexpected number of dimensions.")
+_PARAM_RANKS = (3, 2, 3, 2, 3, 2)      # batched rank of Q, p, G, h, A, b
 
 
 def extract_nBatch(Q, p, G, h, A, b):
-    """Batch size = size(0) of the first fully-batched argument, else 1 (util.py:53-59)."""
-    dims = [3, 2, 3, 2, 3, 2]
-    params = [Q, p, G, h, A, b]
-    for param, dim in zip(params, dims):
-        if param.ndimension() == dim:
-            return param.size(0)
-    return 1
+    """Batch size: size(0) of the first argument given with its batched rank, 1 if none is (util.py:53-59)."""
+    return next((int(t.size(0)) for t, rank in zip((Q, p, G, h, A, b), _PARAM_RANKS) if t.ndimension() == rank), 1)
+
+
+def expandParam(X, nBatch, nDim):
+    """(tensor seen as a batch, was_unbatched) (util.py:44-50).
+
+    0-dim and empty tensors and tensors that already have `nDim` dimensions pass through; one dimension short means
+    "shared by the batch" and becomes a stride-0 view; anything else is the reference's RuntimeError.
+    """
+    have = X.ndimension()
+    if X.nelement() == 0 or have == 0 or have == nDim:
+        return X, False
+    if have + 1 != nDim:
+        raise RuntimeError("Unexpected number of dimensions.")
+    return X.unsqueeze(0).expand(nBatch, *X.shape), True
+
+
+def get_sizes(G, A=None):
+    """(nineq, nz, neq, nBatch) from G (2-D or 3-D) and optionally A; neq is None when A is not given (util.py:22-33)."""
+    if G.dim() not in (2, 3):
+        raise RuntimeError("Unexpected number of dimensions.")
+    nBatch = G.size(0) if G.dim() == 3 else 1
+    nineq, nz = G.shape[-2], G.shape[-1]
+    neq = None if A is None else (A.size(1) if A.nelement() > 0 else 0)
+    return nineq, nz, neq, nBatch
+
+
+def bger(x, y):
+    """Batched outer product: (B,k),(B,l) -> (B,k,l) (util.py:18-19)."""
+    return x[:, :, None] * y[:, None, :]
+
+
+def bdiag(d):
+    """(B,n) -> (B,n,n) with d on the diagonals (util.py:36-41)."""
+    return torch.diag_embed(d)
+
+
+def to_np(t):
+    """Tensor -> numpy (None stays None, empty becomes an empty array) (util.py:9-15)."""
+    if t is None:
+        return None
+    return np.array([]) if t.nelement() == 0 else t.detach().cpu().numpy()
+
+
+def print_header(msg):
+    print('===>', msg)

@@ -69,3 +69,40 @@ def test_util_mirrors_reference_broadcast_rules():
     assert not flag
     with pytest.raises(RuntimeError, match="Unexpected number of dimensions."):
         expandParam(torch.zeros(2, 2, 2, 2), 5, 3)
+
+
+def test_util_helpers_behave_like_qpth_util():
+    """get_sizes / bger / bdiag / to_np (qpth/util.py:9-41), and against the real module when it is on this machine."""
+    import os
+    import sys
+    import types
+    import numpy as np
+    import torch
+    from qpth_b200 import util as U
+    G, A = torch.zeros(4, 3, 5), torch.zeros(4, 2, 5)
+    assert U.get_sizes(G, A) == (3, 5, 2, 4)
+    assert U.get_sizes(G[0]) == (3, 5, None, 1)
+    assert U.get_sizes(G, torch.Tensor()) == (3, 5, 0, 4)
+    x, y = torch.arange(6.).view(2, 3), torch.arange(8.).view(2, 4)
+    assert torch.equal(U.bger(x, y), torch.einsum("bi,bj->bij", x, y))
+    D = U.bdiag(x)
+    assert D.shape == (2, 3, 3) and torch.equal(torch.diagonal(D, dim1=1, dim2=2), x) and D.sum() == x.sum()
+    assert U.to_np(None) is None and U.to_np(torch.Tensor()).size == 0 and np.array_equal(U.to_np(x), x.numpy())
+    if not os.path.isdir("/root/reference/qpth"):
+        return
+    sys.modules.setdefault("cvxpy", types.ModuleType("cvxpy"))     # qpth/solvers/__init__.py imports it eagerly
+    sys.path.insert(0, "/root/reference")
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            from qpth import util as R
+    finally:
+        sys.path.remove("/root/reference")
+    e, Q, q, p = torch.Tensor(), torch.randn(3, 4, 4), torch.randn(4, 4), torch.randn(4)
+    for args in ((Q, p, G[:3, :, :4], torch.randn(3), e, e), (q, p, G[0, :, :4], torch.randn(3), e, e)):
+        assert U.extract_nBatch(*args) == R.extract_nBatch(*args)
+    for X, nd in ((Q, 3), (q, 3), (p, 2), (e, 3), (torch.tensor(1.0), 2)):
+        a, b = U.expandParam(X, 3, nd), R.expandParam(X, 3, nd)
+        assert a[1] == b[1] and a[0].shape == b[0].shape and a[0].stride() == b[0].stride()
+    assert U.get_sizes(G, A) == R.get_sizes(G, A) and torch.equal(U.bdiag(x), R.bdiag(x))
