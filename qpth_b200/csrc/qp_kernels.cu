@@ -808,6 +808,7 @@ __device__ __forceinline__ double2 f_vg_red2_impl(double a, double b, int slot, 
     const int tid = threadIdx.x;
 #if QPB_VG_SMEM
   if (buf >= 0) {
+    named_bar_sync(2, kVG);                                  // buf overlaps vectors the preceding sweep still reads (T1 in f_vec_combine)
     qsm[buf + tid] = a; qsm[buf + kVG + tid] = b;
     named_bar_sync(2, kVG);
     if (tid < 16) {
