@@ -39,5 +39,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
+    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print("built", OUT)

@@ -788,6 +788,7 @@ __device__ __forceinline__ double f_step_fix(double v) { return (isinf(v) && v >
 #ifndef QPB_VECWARP
 #define QPB_VECWARP 0    // measured: 570 vs 531 us forward (profiles/r1_experiments.md); the inline block-wide sweeps stay
 #endif
+#if QPB_VECWARP
 constexpr int kVG = 128;
 enum { CTL_MU = 0, CTL_RESID, CTL_PRI, CTL_DUAL, CTL_ALPHA, CTL_COUNT };
 
@@ -961,6 +962,7 @@ __device__ __noinline__ void f_vec_combine(int w, int t1, int v, int s, int d, i
         if (i >= ep) qsm[s + i] = fma(alpha, qsm[ds + i], qsm[s + i]);
     }
 }
+#endif  // QPB_VECWARP
 }  // namespace fk
 
 __global__ void __launch_bounds__(kThreads, 1)
