@@ -90,7 +90,10 @@ def test_util_helpers_behave_like_qpth_util():
     assert U.to_np(None) is None and U.to_np(torch.Tensor()).size == 0 and np.array_equal(U.to_np(x), x.numpy())
     if not os.path.isdir("/root/reference/qpth"):
         return
-    sys.modules.setdefault("cvxpy", types.ModuleType("cvxpy"))     # qpth/solvers/__init__.py imports it eagerly
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "cvxpy" or k == "qpth" or k.startswith("qpth.")}
+    stubbed = "cvxpy" not in sys.modules
+    if stubbed:
+        sys.modules["cvxpy"] = types.ModuleType("cvxpy")           # qpth/solvers/__init__.py imports it eagerly
     sys.path.insert(0, "/root/reference")
     try:
         import warnings
@@ -99,6 +102,11 @@ def test_util_helpers_behave_like_qpth_util():
             from qpth import util as R
     finally:
         sys.path.remove("/root/reference")
+        for k in [k for k in sys.modules if k == "qpth" or k.startswith("qpth.")]:
+            del sys.modules[k]                                     # leave no reference modules (or stub) behind
+        if stubbed:
+            del sys.modules["cvxpy"]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
     e, Q, q, p = torch.Tensor(), torch.randn(3, 4, 4), torch.randn(4, 4), torch.randn(4)
     for args in ((Q, p, G[:3, :, :4], torch.randn(3), e, e), (q, p, G[0, :, :4], torch.randn(3), e, e)):
         assert U.extract_nBatch(*args) == R.extract_nBatch(*args)
