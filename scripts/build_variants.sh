@@ -11,6 +11,6 @@ if [ "$kind" = timing ]; then dir=build/timing; pre=t_; extra=-DQPB_TIMING; else
 mkdir -p $dir
 for spec in "$@"; do
   name=${spec%%:*}; flags=${spec#*:}
-  ( $B $extra $flags -o $dir/$pre$name.so qpth_b200/csrc/qp_kernels.cu 2>&1 | grep -E "error" ; echo "built $dir/$pre$name.so [$flags]" ) &
+  ( $B $extra $flags -o $dir/$pre$name.so qpth_b200/csrc/qp_kernels.cu 2>&1 | grep -E "error" || true; echo "built $dir/$pre$name.so [$flags]" ) &
 done
 wait
