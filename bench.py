@@ -47,7 +47,7 @@ class ClockSampler:
     """Samples SM clock / throttle reasons of one GPU through NVML (in-process, ~20 us per sample) while the
     timed region runs. (`nvidia-smi -lms` in a subprocess was measurably perturbing launch latency.)"""
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.003):
         self.index, self.period, self.rows, self.ok = index, period, [], False
         self._stop = threading.Event()
         try:
