@@ -56,6 +56,11 @@ typedef struct qpb200_plan {
     int64_t setup_scratch_elems;   /* per system, only when smem_resident == 0 (else 0) */
     int64_t solve_scratch_elems;   /* per QP,     only when smem_resident == 0 (else 0) */
     int64_t setup_smem_bytes, solve_smem_bytes;
+    int64_t coop_smem_bytes;       /* dynamic shared memory of the co-resident solve kernels */
+    int coop_ok;            /* 1: the co-resident kernels exist for this shape (two QPs per SM: W and chol(Q) are read
+                             *    from L2 instead of being staged in shared memory)                                  */
+    int coop;               /* 1: use them (plan_init's default when coop_ok; the caller may clear it to get the
+                             *    one-QP-per-SM kernels, which have the lower latency for a batch smaller than the GPU) */
 } qpb200_plan;
 
 int qpb200_version(void);

@@ -48,6 +48,58 @@ def testpy_problem(nz=10, neq=2, nineq=3, Qscale=1., Gscale=1., Ascale=1.):
 
 
 
+def sweep_spec(i):
+    """Deterministic recipe of sweep case i (dims, conditioning, activity), i in range(N_SWEEP)."""
+    rs = np.random.RandomState(7000 + i)
+    nz = int(rs.randint(5, 121))
+    nineq = int(rs.randint(1, 105))
+    neq = int(rs.choice([0, 0, 1, 3, 8, 20]))
+    neq = min(neq, max(0, nz - 1))                        # A must keep full row rank
+    logk = float([0, 0, 2, 4, 6, 8][i % 6])               # condition number of Q: 10**logk .. (generic when 0)
+    active = bool((i // 6) % 2)                           # pull the unconstrained optimum far outside: many active rows
+    B = 4 if nz * nineq > 4000 else 6
+    return dict(nz=nz, nineq=nineq, neq=neq, logk=logk, active=active, B=B, seed=7000 + i)
+
+
+N_SWEEP = 48
+
+
+def sweep_problem(i):
+    """Randomised parity sweep: nz 5..120, nineq 1..104, neq 0..20, Q with a prescribed
+    condition number up to 1e8 (orthogonal basis x log-spaced spectrum), tight slacks / large p so that the
+    active set is close to nz on the `active` cases.  Everything batched, strictly feasible by construction."""
+    sp = sweep_spec(i)
+    rs = np.random.RandomState(sp["seed"])
+    B, n, m, e = sp["B"], sp["nz"], sp["nineq"], sp["neq"]
+    Q = np.empty((B, n, n))
+    for k in range(B):
+        if sp["logk"] > 0:
+            U, _ = np.linalg.qr(rs.randn(n, n))
+            ev = np.logspace(0.0, -sp["logk"], n)
+            Qk = (U * ev) @ U.T
+            Q[k] = 0.5 * (Qk + Qk.T)
+        else:
+            L = rs.rand(n, n)
+            Q[k] = L @ L.T + 1e-3 * np.eye(n)
+    G = rs.randn(B, m, n)
+    z0 = rs.randn(B, n)
+    s0 = rs.rand(B, m) * (0.05 if sp["active"] else 1.0)
+    p = rs.randn(B, n) * (30.0 if sp["active"] else 1.0)
+    if sp["logk"] > 0:
+        p = p * 10.0 ** (-sp["logk"] / 2)                 # keep |Q^-1 p| moderate for ill-conditioned Q
+    h = np.einsum("bmn,bn->bm", G, z0) + s0
+    A = rs.randn(B, e, n)
+    b = np.einsum("ben,bn->be", A, z0)
+    dl = rs.randn(B, n)
+    return dict(Q=Q, p=p, G=G, h=h, A=A, b=b, dl=dl)
+
+
+def c5_shard(rank, per_rank=1024):
+    """Shard `rank` of BASELINE.json config 5 (B=8192, nz=nineq=100 over 8 ranks): every shard is rebuilt from its
+    own seed, so no rank (and no test) ever materialises the 1.3 GB global batch."""
+    return random_qp_batch(per_rank, 100, 100, 0, seed=5000 + rank)
+
+
 def _testpy(tag_kw):
     def build():
         return testpy_problem(**tag_kw)
@@ -68,7 +120,19 @@ CASES = {
     "testpy_dp": (_testpy(dict(neq=2, nineq=3, Qscale=100., Gscale=100., Ascale=100.)), True),
     "testpy_dG": (_testpy(dict(neq=0, nineq=3)), True),
     "testpy_dA": (_testpy(dict(neq=3, nineq=1)), True),
+    # ---- round 2: BASELINE.json configs at their full sizes, the kernel-selection bands, the randomised sweep
+    "c3": (lambda: random_qp_batch(1024, 50, 50, 10, seed=0), False),
+    "c5_shard0": (lambda: c5_shard(0), False),
+    "band_smem": (lambda: random_qp_batch(6, 20, 120, 0, seed=21), True),        # fast=0, smem_resident=1
+    "band_smem_eq": (lambda: random_qp_batch(6, 24, 116, 4, seed=22), True),
+    "band_setup": (lambda: random_qp_batch(6, 150, 20, 0, seed=23), False),      # fast=1, setup_fast=0
+    "band_setup_eq": (lambda: random_qp_batch(6, 140, 24, 3, seed=24), False),
 }
+for _i in range(N_SWEEP):
+    CASES["sweep%02d" % _i] = ((lambda i=_i: sweep_problem(i)), True)
+
+# cases whose reference run takes more than a few seconds on CPU (kept out of the CPU oracle-vs-golden loops)
+BIG = ("c2", "c4", "c3", "c5_shard0")
 
 
 def load_case(name, golden_dir):

@@ -452,6 +452,172 @@ __device__ __noinline__ void f_trsv_bwd(int A, int ld, int n, int u, int w) {
     }
 }
 
+// ---- substitution on 16-row blocks with INVERTED diagonal blocks ---------------------------------------------
+// Round-1 accounting (profiles/r1z_phase_timing.txt): the three substitutions of a Newton iteration were 40 % of it,
+// 13 block steps each, every thread redoing the same 8 x 8 substitution chain (8 dependent mul+fma links) before its
+// own row update. Here the factorization is followed by f_invert16 (X_k = L_kk^-1 for the 16 x 16 diagonal blocks,
+// ~500 cycles, all blocks in parallel) and a block step becomes  y_k = X_k b_k  (a dot product per lane, every warp
+// computes it for itself: no barrier between it and the row update) followed by the row update: 7 steps instead of
+// 13, one block barrier per step, no dependent chain inside a step.
+// Storage: X_k's strictly lower part TRANSPOSED in the (otherwise unused) upper triangle of its diagonal block,
+// X_k[i][j] (i > j) at M[(k0 + j) * ld + k0 + i]; its diagonal is the reciprocal diagonal already there.
+#ifndef QPB_TRSV16
+#define QPB_TRSV16 1
+#endif
+
+// All 16 x 16 diagonal blocks of the factored n x n matrix at A (n multiple of 8, n <= 256). One half-warp per
+// block, lane c = column c of X_k by forward substitution held in registers. Call with all threads after the
+// factorization's last barrier; the caller synchronises afterwards.
+__device__ __noinline__ void f_invert16(int A, int ld, int n) {
+    QPB_SMEM;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = lane & 15;
+    const int blk = warp + (kNT / 32) * (lane >> 4);
+    const int k0 = 16 * blk;
+    if (k0 < n) {
+        const int bs = min(16, n - k0);
+        double* M = qsm + A + k0 * ld + k0;
+        double x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int ii = (i < bs) ? i : (bs - 1);          // (rows past a short last block: results discarded)
+            const double* Di = M + ii * ld;
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < i; k += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(Di + k);
+                sacc = fma(v.x, x[k], sacc);
+                if (k + 1 < i) sacc = fma(v.y, x[k + 1], sacc);
+            }
+            const double di = Di[ii];
+            x[i] = (i == c) ? di : ((i > c && i < bs) ? -di * sacc : 0.0);
+        }
+        double* xr = M + c * ld;                             // row c of the block: X[i][c] goes to column i > c
+#pragma unroll
+        for (int i = 1; i < 16; ++i)
+            if (i > c && i < bs) xr[i] = x[i];
+    }
+}
+
+// L y = b over all blocks (u = y, b destroyed, b != u); ys: 16 doubles of scratch per warp.
+__device__ __noinline__ void f_trsv16_fwd(int A, int ld, int n, int b, int u, int ys) {
+    QPB_SMEM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = lane & 15, hf = lane >> 4;
+    const double* M = qsm + A;
+    double* yw = qsm + ys + 16 * warp;
+#pragma unroll 1
+    for (int k0 = 0; k0 < n; k0 += 16) {
+        const int bs = min(16, n - k0);
+        // (a) y_k = X_k b_k, every warp for itself: lane (c, hf) sums j in [8 hf, 8 hf + 8), j <= c
+        {
+            const double* Xc = M + k0 * ld + k0 + c;         // X[c][j] at Xc[j * ld]  (j <= c; j == c: the diagonal)
+            const double* bk = qsm + b + k0 + 8 * hf;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < 8; jj += 2) {
+                const int j = 8 * hf + jj;
+                const double2 bv = *reinterpret_cast<const double2*>(bk + jj);
+                const double x0 = (j <= c && c < bs) ? Xc[j * ld] : 0.0;
+                const double x1 = (j + 1 <= c && c < bs) ? Xc[(j + 1) * ld] : 0.0;
+                s0 = fma(x0, (j <= c && c < bs) ? bv.x : 0.0, s0);
+                s1 = fma(x1, (j + 1 <= c && c < bs) ? bv.y : 0.0, s1);
+            }
+            double y = s0 + s1;
+            y += __shfl_xor_sync(0xffffffffu, y, 16);
+            if (hf == 0) {
+                yw[c] = y;
+                if (warp == 0 && c < bs) qsm[u + k0 + c] = y;
+            }
+        }
+        __syncwarp();
+        // (b) rows below the block: b_i -= L[i][k0 .. k0+15] . y_k, two lanes per row (8 columns each)
+        if (bs == 16) {
+            const int pr = tid & 1;
+#pragma unroll 1
+            for (int ib = k0 + 16; ib < n; ib += kNT / 2) {                // block-uniform trip count (shuffle inside)
+                const int i = ib + (tid >> 1);
+                const bool ok = i < n;
+                const double* Li = M + (ok ? i : k0) * ld + k0 + 8 * pr;
+                const double* yy = yw + 8 * pr;
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < 8; jj += 2) {
+                    const double2 lv = *reinterpret_cast<const double2*>(Li + jj);
+                    const double2 yv = *reinterpret_cast<const double2*>(yy + jj);
+                    s0 = fma(lv.x, yv.x, s0);
+                    s1 = fma(lv.y, yv.y, s1);
+                }
+                double sacc = s0 + s1;
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                if (ok && pr == 0) qsm[b + i] -= sacc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// L^T w = u over all blocks (u destroyed, u != w).
+__device__ __noinline__ void f_trsv16_bwd(int A, int ld, int n, int u, int w, int ys) {
+    QPB_SMEM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = lane & 15, hf = lane >> 4;
+    const double* M = qsm + A;
+    double* yw = qsm + ys + 16 * warp;
+#pragma unroll 1
+    for (int k0 = ((n - 1) >> 4) << 4; k0 >= 0; k0 -= 16) {
+        const int bs = min(16, n - k0);
+        // (a) w_k = X_k^T u_k: w_c = sum_{i >= c} X[i][c] u_i, X[i][c] at row (k0 + c), column k0 + i (contiguous in i)
+        {
+            const double* Xr = M + (k0 + c) * ld + k0 + 8 * hf;
+            const double* uk = qsm + u + k0 + 8 * hf;
+            double s0 = 0.0, s1 = 0.0;
+            if (c < bs) {
+#pragma unroll
+                for (int jj = 0; jj < 8; jj += 2) {
+                    const int i = 8 * hf + jj;
+                    if (i + 1 >= c && i < bs) {              // (bs is a multiple of 8: i < bs covers i + 1 too)
+                        const double2 xv = *reinterpret_cast<const double2*>(Xr + jj);
+                        const double2 uv = *reinterpret_cast<const double2*>(uk + jj);
+                        s0 = fma((i >= c) ? xv.x : 0.0, (i >= c) ? uv.x : 0.0, s0);
+                        s1 = fma(xv.y, uv.y, s1);
+                    }
+                }
+            }
+            double y = s0 + s1;
+            y += __shfl_xor_sync(0xffffffffu, y, 16);
+            if (hf == 0) {
+                yw[c] = (c < bs) ? y : 0.0;
+                if (warp == 0 && c < bs) qsm[w + k0 + c] = y;
+            }
+        }
+        __syncwarp();
+        // (b) rows above the block: u_i -= sum_c L[k0 + c][i] w_c, two lanes per row (8 block rows each)
+        {
+            const int pr = tid & 1;
+#pragma unroll 1
+            for (int ib = 0; ib < k0; ib += kNT / 2) {                     // block-uniform trip count (shuffle inside)
+                const int i = ib + (tid >> 1);
+                const bool ok = i < k0;
+                const double* Lc = M + (k0 + 8 * pr) * ld + (ok ? i : 0);
+                const double* yy = yw + 8 * pr;
+                double s0 = 0.0, s1 = 0.0;
+                if (8 * pr < bs) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj += 2) {
+                        s0 = fma(Lc[jj * ld], yy[jj], s0);
+                        s1 = fma(Lc[(jj + 1) * ld], yy[jj + 1], s1);
+                    }
+                }
+                double sacc = s0 + s1;
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                if (ok && pr == 0) qsm[u + i] -= sacc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- product form of the factor: substitution without an intra-block chain -------------------------------
 // f_to_pform rewrites a factored matrix (diagonal blocks: strictly lower = L, diagonal = 1/L_cc) as
 //   T_k  = L_kk^-1      strictly lower part stored TRANSPOSED in the upper triangle of diagonal tile k
@@ -813,6 +979,171 @@ __device__ __noinline__ double f_tri_norm2(int Lp, int n, int x) {
             if (rb != ra) {
 #pragma unroll 2
                 for (int c = l; c <= rb; c += 4) sb = fma(Lb[c], qsm[x + c], sb);
+            }
+        }
+        __syncwarp();                                        // (the row loops above diverge)
+        sa += __shfl_xor_sync(0xffffffffu, sa, 1); sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+        sa += __shfl_xor_sync(0xffffffffu, sa, 2); sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+        if (l == 0) acc = fma(sa, sa, fma(sb, sb, acc));
+    }
+    return acc;
+}
+
+// ---- co-resident mode (two CTAs per SM): W and packed L stay in GLOBAL memory ---------------------------------
+// Shared memory per CTA then holds only the S workspace and the vectors (107 KB at C2), so two QPs share an SM and
+// each one's latency chains (Cholesky pivots, substitutions, reductions) run in the other's bubbles. The passes over
+// W (80 KB) and L (40 KB) become L2 reads: every element is used once per pass, so staging it in shared memory would
+// buy nothing; what matters is the number of loads in flight, hence the register batches below (one L2 round trip
+// per batch). The factors were written by the previous launch and are read-only here: ld.global.nc.
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+// y1 = W x1 (, y2 = W x2). 8 lanes per row (lane j: 16-byte column pairs 2j + 16k), 32 rows per pass, two passes
+// (14 loads) in flight per thread.
+template <bool kTwo>
+__device__ __forceinline__ void g_matvec_rows_impl(const double* __restrict__ Wg, int ld, int rows, int cols, int x1,
+                                                   int x2, int y1, int y2) {
+    QPB_SMEM;
+    const int tid = threadIdx.x, j = tid & 7, rg = tid >> 3;
+#pragma unroll 1
+    for (int rb = 0; rb < rows; rb += 64) {                  // warp-uniform trip count
+        const int r0 = rb + rg, r1 = r0 + 32;
+        const bool ok0 = r0 < rows, ok1 = r1 < rows;
+        const double* p0 = Wg + (size_t)(ok0 ? r0 : 0) * ld;
+        const double* p1 = Wg + (size_t)(ok1 ? r1 : 0) * ld;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;       // row r0: (x1, x2); row r1: (x1, x2)
+#pragma unroll 1
+        for (int cb = 2 * j; cb < cols; cb += 112) {
+            double2 w0[7], w1[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const int c = cb + 16 * k;
+                const bool in = c < cols;
+                w0[k] = in ? ldg2(p0 + c) : make_double2(0.0, 0.0);
+                w1[k] = in ? ldg2(p1 + c) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const int c = cb + 16 * k;
+                if (c < cols) {
+                    const bool hi = c + 1 < cols;             // odd cols: neither W[r][cols] nor x[cols] is ours
+                    double2 u = *reinterpret_cast<const double2*>(qsm + x1 + c);
+                    if (!hi) u.y = 0.0;
+                    const double wy0 = hi ? w0[k].y : 0.0, wy1 = hi ? w1[k].y : 0.0;
+                    a0 = fma(w0[k].x, u.x, a0); a0 = fma(wy0, u.y, a0);
+                    b0 = fma(w1[k].x, u.x, b0); b0 = fma(wy1, u.y, b0);
+                    if (kTwo) {
+                        double2 v = *reinterpret_cast<const double2*>(qsm + x2 + c);
+                        if (!hi) v.y = 0.0;
+                        a1 = fma(w0[k].x, v.x, a1); a1 = fma(wy0, v.y, a1);
+                        b1 = fma(w1[k].x, v.x, b1); b1 = fma(wy1, v.y, b1);
+                    }
+                }
+            }
+        }
+        __syncwarp();                                        // converged warp -> the shuffles take their fast path
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            b0 += __shfl_xor_sync(0xffffffffu, b0, o);
+            if (kTwo) {
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+            }
+        }
+        if (j == 0) {
+            if (ok0) { qsm[y1 + r0] = a0; if (kTwo) qsm[y2 + r0] = a1; }
+            if (ok1) { qsm[y1 + r1] = b0; if (kTwo) qsm[y2 + r1] = b1; }
+        }
+    }
+}
+__device__ __noinline__ void g_matvec_rows2(const double* __restrict__ Wg, int ld, int rows, int cols, int x1, int x2,
+                                            int y1, int y2) {
+    g_matvec_rows_impl<true>(Wg, ld, rows, cols, x1, x2, y1, y2);
+}
+__device__ __noinline__ void g_matvec_rows1(const double* __restrict__ Wg, int ld, int rows, int cols, int x1, int y1) {
+    g_matvec_rows_impl<false>(Wg, ld, rows, cols, x1, 0, y1, 0);
+}
+
+// out[c] = sa * a[c] + sgn * (W^T v)[c] (+ b[c] if b >= 0). A warp owns 16 columns: lane = (row group g, column pair
+// cq), a warp-wide load touches 4 rows x 128 contiguous bytes; the four row groups are summed with two shuffles.
+// Ends with a block barrier (out is complete for every thread).
+__device__ __noinline__ void g_matvec_cols(const double* __restrict__ Wg, int ld, int rows, int cols, int v, int out,
+                                           int a, double sa, int b, double sgn) {
+    QPB_SMEM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 3, cq = lane & 7;
+#pragma unroll 1
+    for (int c0 = 0; c0 < cols; c0 += 16 * (kNT / 32)) {     // warp-uniform trip count
+        const int c = c0 + 16 * warp + 2 * cq;
+        const bool okc = c < cols;
+        const double* pc = Wg + (okc ? c : 0);
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 1
+        for (int rb = g; rb < rows; rb += 4 * 13) {
+            double2 w[13];
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {
+                const int r = rb + 4 * k;
+                w[k] = (r < rows) ? ldg2(pc + (size_t)r * ld) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {
+                const int r = rb + 4 * k;
+                if (r < rows) {
+                    const double vr = qsm[v + r];
+                    s0 = fma(w[k].x, vr, s0);
+                    s1 = fma(w[k].y, vr, s1);
+                }
+            }
+        }
+        __syncwarp();
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        if (g == 0 && okc) {
+            double r0 = sa * qsm[a + c] + sgn * s0;
+            if (b >= 0) r0 += qsm[b + c];
+            qsm[out + c] = r0;
+            if (c + 1 < cols) {
+                double r1 = sa * qsm[a + c + 1] + sgn * s1;
+                if (b >= 0) r1 += qsm[b + c + 1];
+                qsm[out + c + 1] = r1;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// || L x ||^2 partial sums with the packed lower L in global memory: same lane/row pairing as f_tri_norm2.
+__device__ __noinline__ double g_tri_norm2(const double* __restrict__ Lg, int n, int x) {
+    QPB_SMEM;
+    const int tid = threadIdx.x, q4 = tid >> 2, l = tid & 3;
+    double acc = 0.0;
+    const int npairs = (n + 1) >> 1;
+    for (int pb = 0; pb < npairs; pb += kNT / 4) {           // warp-uniform trip count
+        const int pi = pb + q4;
+        const bool act = pi < npairs;
+        const int ra = act ? pi : 0, rb = n - 1 - ra;
+        const double* La = Lg + (ra * (ra + 1)) / 2;
+        const double* Lb = Lg + (rb * (rb + 1)) / 2;
+        double sa = 0.0, sb = 0.0;
+        if (act) {
+#pragma unroll 1
+            for (int cb = l; cb <= rb; cb += 4 * 13) {       // row rb >= row ra: one loop covers both
+                double wa[13], wb[13];
+#pragma unroll
+                for (int k = 0; k < 13; ++k) {
+                    const int c = cb + 4 * k;
+                    wb[k] = (c <= rb) ? __ldg(Lb + c) : 0.0;
+                    wa[k] = (c <= ra && rb != ra) ? __ldg(La + c) : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < 13; ++k) {
+                    const int c = cb + 4 * k;
+                    if (c <= rb) {
+                        const double xc = qsm[x + c];
+                        sb = fma(wb[k], xc, sb);
+                        sa = fma(wa[k], xc, sa);
+                    }
+                }
             }
         }
         __syncwarp();                                        // (the row loops above diverge)

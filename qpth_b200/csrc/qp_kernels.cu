@@ -27,6 +27,10 @@ using namespace qpb;
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef QPB_COOP_DEFAULT
+#define QPB_COOP_DEFAULT 1     // plan_init selects the co-resident kernels whenever the shape allows (plan->coop)
+#endif
+constexpr int kCoopDefault = QPB_COOP_DEFAULT;
 constexpr int kMaxSmem = 232448 - 1024;   // 227 KB opt-in limit per CTA on sm_100, minus static smem slack
 
 struct KDims {
@@ -671,27 +675,32 @@ struct FLayout {              // offsets in doubles into the dynamic shared arra
     int vl;
 };
 __host__ __device__ inline int fast_vl(int n, int msp) { return ((n > msp ? n : msp) + 7) & ~7; }
-__host__ __device__ inline FLayout fast_layout(const KDims& D) {
+// coop = co-resident mode: W and packed L are NOT staged (they are read from global memory, qp_fast.cuh); the
+// packed L visits the S workspace twice (whitening at entry, un-whitening at exit), so Lp aliases LS.
+__host__ __device__ inline FLayout fast_layout(const KDims& D, bool coop) {
     FLayout L;
     L.vl = fast_vl(D.n, D.msp);
     L.W = 0;
-    L.LS = L.W + D.ms * D.ldw;
-    L.Lp = L.LS + D.msp * D.lds;
-    L.vec = L.Lp + D.lp;
+    L.LS = coop ? 0 : L.W + D.ms * D.ldw;
+    L.Lp = coop ? L.LS : L.LS + D.msp * D.lds;
+    L.vec = coop ? L.LS + D.msp * D.lds : L.Lp + D.lp;
     L.red = L.vec + F_COUNT * L.vl;
     L.bar = L.red + kRedDoubles;
     L.tab = L.bar + 2;
     return L;
 }
-__host__ __device__ inline size_t fast_smem_doubles(const KDims& D) {
-    const FLayout L = fast_layout(D);
+__host__ __device__ inline size_t fast_smem_doubles(const KDims& D, bool coop) {
+    const FLayout L = fast_layout(D, coop);
     return (size_t)L.tab + kTabDoubles;
 }
 
 struct FCtx {
     FLayout L;
     const double* Kg;
+    const double* Wg;     // co-resident mode: W and packed L in global memory
+    const double* Lg;
     uint32_t kphase;
+    uint32_t lphase;      // parity of the next completion on bar[0] (W/L staging)
     bool kpending;
 };
 #define FV(i) (C.L.vec + (i) * C.L.vl)
@@ -716,17 +725,35 @@ __device__ __forceinline__ void f_wait_K(FCtx& C) {
     C.kpending = false;
 }
 
+// Co-resident mode: bring the packed L into the (currently dead) S workspace. Call with all threads after a block
+// barrier that retired every reader of the workspace and with no K copy in flight; returns when L has landed.
+__device__ __forceinline__ void f_stage_L(const KDims& D, FCtx& C) {
+    QPB_SMEM;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(qsm + C.L.bar);
+    if (threadIdx.x == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, (uint32_t)(D.lp * 8));
+        bulk_issue_thread(qsm + C.L.Lp, C.Lg, (uint32_t)(D.lp * 8), bar);
+    }
+    mbar_wait(bar, C.lphase);
+    C.lphase ^= 1u;
+}
+
 // Stage W and packed L with TMA, start the first K copy, build the tile table.
+// kCoop: only L is staged (into the S workspace, for the whitening of the caller's first vector); the caller issues
+// the first K copy itself once it is done with L (f_issue_K after a block barrier).
+template <bool kCoop>
 __device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double* Lfac, const double* Wfac,
                                            const double* Kfac, int sF) {
     QPB_SMEM;
     FCtx C;
-    C.L = fast_layout(D);
+    C.L = fast_layout(D, kCoop);
     const int64_t sys = sF ? qp : 0;
-    const double* Lg = Lfac + sys * (int64_t)D.lp;
-    const double* Wg = Wfac + sys * (int64_t)D.ms * D.ldw;
+    C.Lg = Lfac + sys * (int64_t)D.lp;
+    C.Wg = Wfac + sys * (int64_t)D.ms * D.ldw;
     C.Kg = Kfac + sys * (int64_t)D.msp * D.lds;
     C.kphase = 0;
+    C.lphase = 0;
     C.kpending = false;
     const int tid = threadIdx.x;
     uint64_t* bar = reinterpret_cast<uint64_t*>(qsm + C.L.bar);
@@ -736,17 +763,39 @@ __device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double*
     }
     build_tile_table(reinterpret_cast<uint16_t*>(qsm + C.L.tab), (D.msp - D.ep) >> 3, tid);
     __syncthreads();
-    if (tid == 0) {
-        const uint32_t wb = (uint32_t)(D.ms * D.ldw * 8), lb = (uint32_t)(D.lp * 8);
-        mbar_expect_tx(bar, wb + lb);
-        bulk_issue_thread(qsm + C.L.W, Wg, wb, bar);
-        bulk_issue_thread(qsm + C.L.Lp, Lg, lb, bar);
+    if (kCoop) {
+        f_stage_L(D, C);
+    } else {
+        if (tid == 0) {
+            const uint32_t wb = (uint32_t)(D.ms * D.ldw * 8), lb = (uint32_t)(D.lp * 8);
+            mbar_expect_tx(bar, wb + lb);
+            bulk_issue_thread(qsm + C.L.W, C.Wg, wb, bar);
+            bulk_issue_thread(qsm + C.L.Lp, C.Lg, lb, bar);
+        }
+        f_issue_K(D, C);
+        mbar_wait(bar, 0);
     }
-    f_issue_K(D, C);
-    mbar_wait(bar, 0);
     // reciprocal diagonals of L (packed) and of the pre-factored equality block
     _Pragma("unroll 1") for (int i = tid; i < D.n; i += kNT) qsm[FV(F_DINVL) + i] = 1.0 / qsm[C.L.Lp + (i * (i + 1)) / 2 + i];
     return C;
+}
+
+// mat-vec dispatch: shared-memory resident W / L, or the global-memory passes of the co-resident mode
+template <bool kCoop>
+__device__ __forceinline__ void mv_rows1(const KDims& D, const FCtx& C, int x1, int y1) {
+    if (kCoop) g_matvec_rows1(C.Wg, D.ldw, D.ms, D.n, x1, y1);
+    else f_matvec_rows1(C.L.W, D.ldw, D.ms, D.n, x1, y1);
+}
+template <bool kCoop>
+__device__ __forceinline__ void mv_rows2(const KDims& D, const FCtx& C, int x1, int x2, int y1, int y2) {
+    if (kCoop) g_matvec_rows2(C.Wg, D.ldw, D.ms, D.n, x1, x2, y1, y2);
+    else f_matvec_rows2(C.L.W, D.ldw, D.ms, D.n, x1, x2, y1, y2);
+}
+template <bool kCoop>
+__device__ __forceinline__ void mv_cols(const KDims& D, const FCtx& C, int v, int p0, int p1, int out, int a, double sa,
+                                        int b, double sgn) {
+    if (kCoop) g_matvec_cols(C.Wg, D.ldw, D.ms, D.n, v, out, a, sa, b, sgn);
+    else f_matvec_cols(C.L.W, D.ldw, D.ms, D.n, v, p0, p1, out, a, sa, b, sgn);
 }
 
 // factor_kkt + first half of solve_kkt: F_AUG = -h_full (pad entries 0), F_D = d  ->  F_W = -S^-1 h_full
@@ -772,200 +821,25 @@ __device__ __forceinline__ void f_factor_and_solve(const KDims& D, FCtx& C, bool
     } else
 #endif
     {
+#if QPB_TRSV16
+        f_invert16(C.L.LS, D.lds, D.msp);
+        __syncthreads();
+        QPB_TICK(28);   // inverted 16 x 16 diagonal blocks
+        f_trsv16_bwd(C.L.LS, D.lds, D.msp, FV(F_AUG), FV(F_W), C.L.red);
+#else
         f_trsv_bwd(C.L.LS, D.lds, D.msp, FV(F_AUG), FV(F_W));
+#endif
     }
     QPB_TICK(33);   // backward substitution
 }
 
 __device__ __forceinline__ double f_step_fix(double v) { return (isinf(v) && v > 0.0) ? 1.0 : v; }
 
-// ---- the "vector group": all O(m) step logic of one Newton iteration on warps 0..3 ---------------------------
-// The vectors of the reduced system have ms <= 224 entries: thread t < 128 owns entries t, t + 128. The four warps
-// sit on the four SM sub-partitions, reduce with shuffles + one 128-thread named barrier (no block-wide barrier,
-// no two-barrier shared-memory reduction per min / sum) and run dependent sweeps back to back; warps 4..7 wait at
-// the next __syncthreads. Scalars go through ctl[] (shared memory). fp64 divide / sqrt and the reductions are
-// shared subroutines: inlined, the three routines were 60 KB of SASS and ran at the speed of instruction fetch.
-#ifndef QPB_VECWARP
-#define QPB_VECWARP 0    // measured: 570 vs 531 us forward (profiles/r1_experiments.md); the inline block-wide sweeps stay
-#endif
-#if QPB_VECWARP
-constexpr int kVG = 128;
-enum { CTL_MU = 0, CTL_RESID, CTL_PRI, CTL_DUAL, CTL_ALPHA, CTL_COUNT };
-
-__device__ __noinline__ double f_div(double a, double b) { return a / b; }
-__device__ __noinline__ double f_sqrt(double a) { return sqrt(a); }
-__device__ __forceinline__ double f_cand(double v, double dv) { return (dv > 0.0) ? INFINITY : f_div(-v, dv); }
-
-// reductions over the vector group. Two implementations:
-//  QPB_VG_SMEM = 0: shuffles inside each warp, 8 doubles at `slot` to combine the four warps;
-//  QPB_VG_SMEM = 1: no shuffles - every thread parks its partials in `buf` (2 x 128 + 16 doubles: the dead
-//                   AUG/T0/T1 vector slots), 16 threads add 16 entries each, everybody adds the 8 partial sums.
-#ifndef QPB_VG_SMEM
-#define QPB_VG_SMEM 0
-#endif
-template <bool kMin>
-__device__ __forceinline__ double2 f_vg_red2_impl(double a, double b, int slot, int buf) {
-    QPB_SMEM;
-    const int tid = threadIdx.x;
-#if QPB_VG_SMEM
-  if (buf >= 0) {
-    named_bar_sync(2, kVG);                                  // buf overlaps vectors the preceding sweep still reads (T1 in f_vec_combine)
-    qsm[buf + tid] = a; qsm[buf + kVG + tid] = b;
-    named_bar_sync(2, kVG);
-    if (tid < 16) {
-        const double* src = qsm + buf + (tid >> 3) * kVG + (tid & 7);
-        double x0 = src[0], x1 = src[8];
-#pragma unroll
-        for (int j = 2; j < 16; j += 2) {
-            x0 = kMin ? fmin(x0, src[8 * j]) : x0 + src[8 * j];
-            x1 = kMin ? fmin(x1, src[8 * j + 8]) : x1 + src[8 * j + 8];
-        }
-        qsm[buf + 2 * kVG + tid] = kMin ? fmin(x0, x1) : x0 + x1;
-    }
-    named_bar_sync(2, kVG);
-    const double2 p0 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG), p1 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 2),
-                  p2 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 4), p3 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 6),
-                  q0 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 8), q1 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 10),
-                  q2 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 12), q3 = *reinterpret_cast<const double2*>(qsm + buf + 2 * kVG + 14);
-    named_bar_sync(2, kVG);                                  // buf may be reused by the next reduction right away
-    if (kMin) return make_double2(fmin(fmin(fmin(p0.x, p0.y), fmin(p1.x, p1.y)), fmin(fmin(p2.x, p2.y), fmin(p3.x, p3.y))),
-                                  fmin(fmin(fmin(q0.x, q0.y), fmin(q1.x, q1.y)), fmin(fmin(q2.x, q2.y), fmin(q3.x, q3.y))));
-    return make_double2(((p0.x + p0.y) + (p1.x + p1.y)) + ((p2.x + p2.y) + (p3.x + p3.y)),
-                        ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y)));
-  }
-#endif
-    const int lane = tid & 31, warp = tid >> 5;
-    QPB_TICK(18);   // (entry: whatever preceded the call)
-    a = kMin ? warp_min(a) : warp_sum(a); b = kMin ? warp_min(b) : warp_sum(b);
-    QPB_TICK(19);   // two warp reductions
-    if (lane == 0) { qsm[slot + warp] = a; qsm[slot + 4 + warp] = b; }
-    named_bar_sync(2, kVG);
-    QPB_TICK(22);   // named barrier (128 threads)
-    const double2 a0 = *reinterpret_cast<const double2*>(qsm + slot), a1 = *reinterpret_cast<const double2*>(qsm + slot + 2);
-    const double2 b0 = *reinterpret_cast<const double2*>(qsm + slot + 4), b1 = *reinterpret_cast<const double2*>(qsm + slot + 6);
-    if (kMin) return make_double2(fmin(fmin(a0.x, a0.y), fmin(a1.x, a1.y)), fmin(fmin(b0.x, b0.y), fmin(b1.x, b1.y)));
-    return make_double2((a0.x + a0.y) + (a1.x + a1.y), (b0.x + b0.y) + (b1.x + b1.y));
-}
-__device__ __noinline__ double2 f_vg_sum2(double a, double b, int slot, int buf) { return f_vg_red2_impl<false>(a, b, slot, buf); }
-__device__ __noinline__ double2 f_vg_min2(double a, double b, int slot, int buf) { return f_vg_red2_impl<true>(a, b, slot, buf); }
-
-// residuals (batch.py:94-107) + d = z/s and the affine right-hand side (batch.py:109,150).
-// in: rv = W x~, hW = W r~x, tri[0..7] = per-warp partial sums of |L r~x|^2.  out: rv = [ry; rz], d, aug, ctl[].
-// scr: 16 doubles of scratch.
-__device__ __noinline__ void f_vec_resid(int rv, int hb, int s, int v, int hW, int d, int aug, int tri, int ctl,
-                                         int scr, int buf, int ep, int ms, double dm) {
-    QPB_SMEM;
-    const int tid = threadIdx.x;
-    double a0 = 0.0, a1 = 0.0, a3 = 0.0;
-#pragma unroll 1
-    for (int i = tid; i < ms; i += kVG) {
-        const double si = (i >= ep) ? qsm[s + i] : 0.0;
-        const double r = qsm[rv + i] - qsm[hb + i] + si;
-        qsm[rv + i] = r;
-        if (i < ep) a0 = fma(r, r, a0);
-        else { a1 = fma(r, r, a1); a3 = fma(si, qsm[v + i], a3); }
-    }
-    double a2 = (tid < kNT / 32) ? qsm[tri + tid] : 0.0;
-    QPB_TICK(34);
-    const double2 r01 = f_vg_sum2(a0, a1, scr, buf), r23 = f_vg_sum2(a2, a3, scr + 8, buf);
-    a0 = r01.x; a1 = r01.y; a2 = r23.x; a3 = r23.y;
-    QPB_TICK(35);
-    const double mu = fabs(f_div(a3, dm));
-    QPB_TICK(23);   // one f_div call
-    const double pri = f_sqrt(a1) + f_sqrt(a0), dual = f_sqrt(a2);
-    if (tid == 0) {
-        qsm[ctl + CTL_MU] = mu; qsm[ctl + CTL_RESID] = pri + dual + dm * mu;
-        qsm[ctl + CTL_PRI] = pri; qsm[ctl + CTL_DUAL] = dual;
-    }
-    QPB_TICK(36);
-#pragma unroll 1
-    for (int i = tid; i < ms; i += kVG) {
-        double hfull = qsm[hW + i] - qsm[rv + i];
-        if (i >= ep) {
-            const double vi = qsm[v + i];
-            const double di = f_div(vi, qsm[s + i]);
-            qsm[d + i] = di;
-            hfull += f_div(vi, di);
-        }
-        qsm[aug + i] = -hfull;
-    }
-}
-
-// affine step length, sigma, corrector right-hand side (batch.py:160-181). in: w = [dy_aff; dz_aff].
-// out: dsa, ds (= corrector rs), t1 (= right-hand side of the corrector solve, all msp entries).
-__device__ __noinline__ void f_vec_affine(int w, int v, int s, int d, int dsa, int ds, int t1, int scr, int buf, int ep,
-                                          int ms, int msp, double mu) {
-    QPB_SMEM;
-    const int tid = threadIdx.x;
-    double mn0 = INFINITY, mn1 = INFINITY;
-#pragma unroll 1
-    for (int i = ep + tid; i < ms; i += kVG) {
-        const double dz = qsm[w + i], vi = qsm[v + i];
-        const double dsi = f_div(-vi - dz, qsm[d + i]);
-        qsm[dsa + i] = dsi;
-        mn0 = fmin(mn0, f_cand(vi, dz));
-        mn1 = fmin(mn1, f_cand(qsm[s + i], dsi));
-    }
-    QPB_TICK(41);
-    const double2 mn = f_vg_min2(mn0, mn1, scr, buf);
-    QPB_TICK(43);
-    const double alpha = fmin(fmin(f_step_fix(mn.x), f_step_fix(mn.y)), 1.0);
-    double sm0 = 0.0, sm1 = 0.0;
-#pragma unroll 1
-    for (int i = ep + tid; i < ms; i += kVG) {
-        const double si = qsm[s + i], vi = qsm[v + i];
-        sm0 = fma(si + alpha * qsm[dsa + i], vi + alpha * qsm[w + i], sm0);
-        sm1 = fma(si, vi, sm1);
-    }
-    const double2 sm = f_vg_sum2(sm0, sm1, scr + 8, buf);
-    const double sr = f_div(sm.x, sm.y);
-    const double musig = mu * (sr * sr * sr);
-    QPB_TICK(45);
-#pragma unroll 1
-    for (int i = tid; i < msp; i += kVG) {
-        double rhs = 0.0;
-        if (i >= ep && i < ms) {
-            const double rsc = f_div(-musig + qsm[dsa + i] * qsm[w + i], qsm[s + i]);
-            qsm[ds + i] = rsc;
-            rhs = -f_div(rsc, qsm[d + i]);
-        }
-        qsm[t1 + i] = rhs;
-    }
-}
-
-// combined direction, step length, update of [y; z] and s (batch.py:185-203). in: t1 = [dy_cor; dz_cor].
-// out: w = [dy; dz], ds, v += alpha dv, s += alpha ds, ctl[CTL_ALPHA] (x~ is updated by the caller after W^T dv).
-__device__ __noinline__ void f_vec_combine(int w, int t1, int v, int s, int d, int dsa, int ds, int ctl, int scr,
-                                           int buf, int ep, int ms) {
-    QPB_SMEM;
-    const int tid = threadIdx.x;
-    double mn0 = INFINITY, mn1 = INFINITY;
-#pragma unroll 1
-    for (int i = tid; i < ms; i += kVG) {
-        const double wci = qsm[t1 + i];
-        const double dv = qsm[w + i] + wci;
-        qsm[w + i] = dv;
-        if (i >= ep) {
-            const double dsc = f_div(-qsm[ds + i] - wci, qsm[d + i]);
-            const double dsi = qsm[dsa + i] + dsc;
-            qsm[ds + i] = dsi;
-            mn0 = fmin(mn0, f_cand(qsm[v + i], dv));
-            mn1 = fmin(mn1, f_cand(qsm[s + i], dsi));
-        }
-    }
-    const double2 mn = f_vg_min2(mn0, mn1, scr, buf);
-    const double alpha = fmin(0.999 * fmin(f_step_fix(mn.x), f_step_fix(mn.y)), 1.0);
-    if (tid == 0) qsm[ctl + CTL_ALPHA] = alpha;
-#pragma unroll 1
-    for (int i = tid; i < ms; i += kVG) {
-        qsm[v + i] = fma(alpha, qsm[w + i], qsm[v + i]);
-        if (i >= ep) qsm[s + i] = fma(alpha, qsm[ds + i], qsm[s + i]);
-    }
-}
-#endif  // QPB_VECWARP
 }  // namespace fk
 
-__global__ void __launch_bounds__(kThreads, 1)
+// kCoop: co-resident mode (two CTAs per SM; W and L read from global memory, see qp_fast.cuh).
+template <bool kCoop>
+__global__ void __launch_bounds__(kThreads, kCoop ? 2 : 1)
 k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* __restrict__ h, int64_t sh,
                const double* __restrict__ b, int64_t sb, const double* __restrict__ Lfac,
                const double* __restrict__ Wfac, const double* __restrict__ Kfac, int sF, double eps,
@@ -982,9 +856,8 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     if (threadIdx.x == 0) { for (int i = 0; i < 128; ++i) s_tim[i] = 0; s_tim[128] = clock64(); s_tim2 = s_tim[128]; }
     __syncthreads();
 #endif
-    FCtx C = f_make_ctx(D, qp, Lfac, Wfac, Kfac, sF);
+    FCtx C = f_make_ctx<kCoop>(D, qp, Lfac, Wfac, Kfac, sF);
     QPB_TICK(0);
-    const int W = C.L.W, ldw = D.ldw;
     const int pt = FV(F_PT), xt = FV(F_XT), rxt = FV(F_RXT), s = FV(F_S), v = FV(F_V), rv = FV(F_RV),
               hW = FV(F_HW), w = FV(F_W), dsa = FV(F_DSA), ds = FV(F_DS), d = FV(F_D), hb = FV(F_HB),
               aug = FV(F_AUG), t0 = FV(F_T0), t1 = FV(F_T1);
@@ -1007,16 +880,20 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     __syncthreads();
     QPB_TICK(1);
     f_whiten(C.L.Lp, n, FV(F_DINVL), t1, pt);                   // p~ = L^-1 p
+    if (kCoop) {                                                // L leaves the S workspace: the first K copy may land
+        __syncthreads();
+        f_issue_K(D, C);
+    }
     QPB_TICK(2);
 
     // ---- initial point: solve_kkt(p, 0, -h, -b) with d = 1   (batch.py:61-67)
-    f_matvec_rows1(W, ldw, ms, n, pt, hW);
+    mv_rows1<kCoop>(D, C, pt, hW);
     __syncthreads();
     _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) qsm[aug + i] = -(qsm[hW + i] + qsm[hb + i]);
     __syncthreads();
     f_factor_and_solve(D, C, false);
     f_issue_K(D, C);
-    f_matvec_cols(W, ldw, ms, n, w, t0, t1, xt, pt, -1.0, -1, -1.0);   // x~ = -p~ - W^T w
+    mv_cols<kCoop>(D, C, w, t0, t1, xt, pt, -1.0, -1, -1.0);   // x~ = -p~ - W^T w
     {
         double mn[2] = {INFINITY, INFINITY};
         _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) {
@@ -1039,113 +916,13 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     double best = 0.0, ret_resid = 0.0;
     int nNot = 0, iters_run = 0;
     const double dm = (double)m;
-#if QPB_VECWARP
-    const int tri = C.L.red + 104, ctl = C.L.red + 112, vscr = C.L.red;   // (red[0..103] is reduction scratch)
-    const int vbuf = (3 * C.L.vl >= 2 * kVG + 16) ? aug : -1;   // AUG|T0|T1 (contiguous, dead inside the vector-group sweeps)
     for (int it = 0; it < maxIter; ++it) {
         iters_run = it + 1;
         // ---- residuals (batch.py:94-107)
         QPB_TICK(3);
-        f_matvec_cols(W, ldw, ms, n, v, t0, t1, rxt, xt, 1.0, pt, 1.0);      // r~x = x~ + p~ + W^T [y;z]
+        mv_cols<kCoop>(D, C, v, t0, t1, rxt, xt, 1.0, pt, 1.0);      // r~x = x~ + p~ + W^T [y;z]
         QPB_TICK(4);
-#ifdef QPB_TIMING_REPEAT   // cold vs warm cost of idempotent phases (instruction-cache experiment)
-        f_matvec_cols(W, ldw, ms, n, v, t0, t1, rxt, xt, 1.0, pt, 1.0); QPB_TICK(61);
-        f_matvec_cols(W, ldw, ms, n, v, t0, t1, rxt, xt, 1.0, pt, 1.0); QPB_TICK(62);
-#endif
-        f_matvec_rows2(W, ldw, ms, n, xt, rxt, rv, hW);                      // W x~ , W r~x
-        QPB_TICK(5);
-#ifdef QPB_TIMING_PROBES   // cost of warp-collective instructions in this kernel's context (slots 61-63, 77-79)
-        {
-            __syncthreads();
-            QPB_TICK(60);
-            double pv = qsm[xt + (tid & 63)], pw = qsm[rxt + (tid & 63)];
-            pv = warp_sum(pv); pw = warp_sum(pw); pv = warp_sum(pv); pw = warp_sum(pw);   // 4 warp sums, all 8 warps
-            QPB_TICK(61);
-            if (tid < 128) { pv = warp_sum(pv); pw = warp_sum(pw); pv = warp_sum(pv); pw = warp_sum(pw); }   // warps 0..3 only
-            QPB_TICK(62);
-            if (tid < 128) { pv = warp_min(pv); pw = warp_min(pw); pv = warp_min(pv); pw = warp_min(pw); }
-            QPB_TICK(63);
-            double c0 = pv, c1 = pw;
-            for (int r = 0; r < 8; ++r) { dmma884(c0, c1, pv, pw); dmma884(c0, c1, pw, pv); }            // 16 dependent DMMAs, all warps
-            QPB_TICK(77);
-            if (tid < 32) for (int r = 0; r < 8; ++r) { dmma884(c0, c1, pv, pw); dmma884(c0, c1, pw, pv); } // warp 0 alone
-            QPB_TICK(78);
-            for (int r = 0; r < 16; ++r) { c0 = fma(c0, pv, pw); c1 = fma(c1, pw, pv); }                 // 16 dependent DFMA pairs
-            QPB_TICK(79);
-            if (c0 + c1 == 1.2345e301) qsm[t0] = c0;                                                      // keep the results alive
-            __syncthreads();
-            QPB_TICK(93);
-        }
-#endif
-#ifdef QPB_TIMING_REPEAT
-        __syncthreads();
-        f_matvec_rows2(W, ldw, ms, n, xt, rxt, rv, hW); __syncthreads(); QPB_TICK(77);
-        f_matvec_rows2(W, ldw, ms, n, xt, rxt, rv, hW); __syncthreads(); QPB_TICK(78);
-        { double z1 = f_tri_norm2(C.L.Lp, n, rxt); if (z1 == -1.0) qsm[0] = z1; } __syncthreads(); QPB_TICK(93);
-        { double z1 = f_tri_norm2(C.L.Lp, n, rxt); if (z1 == -1.0) qsm[0] = z1; } __syncthreads(); QPB_TICK(94);
-#endif
-        {
-            const double tp = warp_sum(f_tri_norm2(C.L.Lp, n, rxt));         // |L r~x|^2 = |Qx + p + G^T z + A^T y|^2
-            if ((tid & 31) == 0) qsm[tri + (tid >> 5)] = tp;
-        }
-        __syncthreads();
-        QPB_TICK(7);
-        if (tid < kVG) f_vec_resid(rv, hb, s, v, hW, d, aug, tri, ctl, vscr, vbuf, ep, ms, dm);
-        __syncthreads();
-        QPB_TICK(6);
-        const double mu = qsm[ctl + CTL_MU], resid = qsm[ctl + CTL_RESID];
-        if (trace != nullptr && tid == 0) {                     // what verbose=1 prints (batch.py:115-117)
-            double* tr = trace + ((int64_t)qp * maxIter + it) * 4;
-            tr[0] = qsm[ctl + CTL_PRI]; tr[1] = qsm[ctl + CTL_DUAL]; tr[2] = mu; tr[3] = resid;
-        }
-        // ---- best-iterate tracking and exit tests (batch.py:118-143), per QP (see k_forward)
-        const bool improved = (it == 0) || (resid < best);
-        if (improved) { best = resid; nNot = 0; } else { ++nNot; }
-        if (improved || resid < best_tie * best) {
-            ret_resid = resid;
-            _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[FV(F_BXT) + i] = qsm[xt + i];
-            _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) { qsm[FV(F_BS) + i] = qsm[s + i]; qsm[FV(F_BV) + i] = qsm[v + i]; }
-        }
-        if ((nNot == notImprovedLim && best < stall_tol) || best < eps || mu > 1e32) break;
-        if (!(resid == resid) || isinf(resid)) break;
-        QPB_TICK(9);
-        // ---- factor_kkt with d = z/s and the affine right-hand side (batch.py:109-113,150): d, aug set by f_vec_resid
-        f_factor_and_solve(D, C, true);                               // w = [dy_aff; dz_aff]
-        QPB_TICK(10);
-        if (tid < kVG) f_vec_affine(w, v, s, d, dsa, ds, t1, vscr + 16, vbuf, ep, ms, msp, mu);      // batch.py:160-181
-        __syncthreads();
-        QPB_TICK(11);
-#if QPB_PFORM
-        f_ptrsv_fwd(C.L.LS, D.lds, msp, t1, t0);
-        QPB_TICK(12);
-        f_ptrsv_bwd(C.L.LS, D.lds, msp, t0, t1);                 // t1 = [dy_cor; dz_cor]
-#else
-        f_trsv_fwd(C.L.LS, D.lds, msp, 0, msp, t1, t0);
-        QPB_TICK(12);
-        f_trsv_bwd(C.L.LS, D.lds, msp, t0, t1);                  // t1 = [dy_cor; dz_cor]
-#endif
-        QPB_TICK(13);
-        f_issue_K(D, C);                                         // next factor_kkt's K copy overlaps the rest
-        // ---- combined direction, step length, update (batch.py:185-203)
-        if (tid < kVG) f_vec_combine(w, t1, v, s, d, dsa, ds, ctl, vscr + 32, vbuf, ep, ms);
-        __syncthreads();
-        QPB_TICK(14);
-        f_matvec_cols(W, ldw, ms, n, w, t0, t1, hW, rxt, -1.0, -1, -1.0);     // dx~ = -r~x - W^T dv  (in hW)
-        QPB_TICK(15);
-        {
-            const double alpha = qsm[ctl + CTL_ALPHA];
-            _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[xt + i] = fma(alpha, qsm[hW + i], qsm[xt + i]);
-        }
-        __syncthreads();
-    }
-#else
-    for (int it = 0; it < maxIter; ++it) {
-        iters_run = it + 1;
-        // ---- residuals (batch.py:94-107)
-        QPB_TICK(3);
-        f_matvec_cols(W, ldw, ms, n, v, t0, t1, rxt, xt, 1.0, pt, 1.0);      // r~x = x~ + p~ + W^T [y;z]
-        QPB_TICK(4);
-        f_matvec_rows2(W, ldw, ms, n, xt, rxt, rv, hW);                      // W x~ , W r~x
+        mv_rows2<kCoop>(D, C, xt, rxt, rv, hW);                      // W x~ , W r~x
         __syncthreads();
         QPB_TICK(5);
         double acc[4] = {0.0, 0.0, 0.0, 0.0};                   // |ry|^2, |rz|^2, |L r~x|^2, s.z
@@ -1156,7 +933,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
             else { acc[1] = fma(r, r, acc[1]); acc[3] = fma(qsm[s + i], qsm[v + i], acc[3]); }
         }
         QPB_TICK(6);
-        acc[2] = f_tri_norm2(C.L.Lp, n, rxt);
+        acc[2] = kCoop ? g_tri_norm2(C.Lg, n, rxt) : f_tri_norm2(C.L.Lp, n, rxt);
         QPB_TICK(7);
         f_reduce_sum4(acc, C.L.red);
         QPB_TICK(8);
@@ -1227,6 +1004,10 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         f_ptrsv_fwd(C.L.LS, D.lds, msp, t1, t0);
         QPB_TICK(12);
         f_ptrsv_bwd(C.L.LS, D.lds, msp, t0, t1);                 // t1 = [dy_cor; dz_cor]
+#elif QPB_TRSV16
+        f_trsv16_fwd(C.L.LS, D.lds, msp, t1, t0, C.L.red);
+        QPB_TICK(12);
+        f_trsv16_bwd(C.L.LS, D.lds, msp, t0, t1, C.L.red);       // t1 = [dy_cor; dz_cor]
 #else
         f_trsv_fwd(C.L.LS, D.lds, msp, 0, msp, t1, t0);
         QPB_TICK(12);
@@ -1250,7 +1031,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         }
         __syncthreads();
         QPB_TICK(14);
-        f_matvec_cols(W, ldw, ms, n, w, t0, t1, hW, rxt, -1.0, -1, -1.0);     // dx~ = -r~x - W^T dv  (in hW)
+        mv_cols<kCoop>(D, C, w, t0, t1, hW, rxt, -1.0, -1, -1.0);     // dx~ = -r~x - W^T dv  (in hW)
         QPB_TICK(15);
         f_reduce_min2(mn, C.L.red);
         {
@@ -1263,11 +1044,15 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         }
         __syncthreads();
     }
-#endif
 
     // ---- outputs: x = L^-T x~_best, y, z, s of the returned iterate (batch.py:205-207)
     __syncthreads();
     QPB_TICK(16);
+    if (kCoop) {                                                 // the S workspace is dead: L comes back for x = L^-T x~
+        if (C.kpending) f_wait_K(C);
+        __syncthreads();
+        f_stage_L(D, C);
+    }
     f_unwhiten(C.L.Lp, n, FV(F_DINVL), FV(F_BXT), t0);
     if (C.kpending) f_wait_K(C);                                 // drain the in-flight copy before exit
     _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) zhat[(int64_t)qp * n + i] = qsm[t0 + i];
@@ -1286,8 +1071,8 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
 #endif
 }
 
-template <bool kBackward>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kBackward, bool kCoop>
+__global__ void __launch_bounds__(kThreads, kCoop ? 2 : 1)
 k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ rx_in,
            const double* __restrict__ rs_in, const double* __restrict__ rz_in,
            const double* __restrict__ ry_in, const double* __restrict__ zhat,
@@ -1301,8 +1086,7 @@ k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ 
     const int tid = threadIdx.x;
     const int qp = blockIdx.x;
     const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
-    FCtx C = f_make_ctx(D, qp, Lfac, Wfac, Kfac, sF);
-    const int W = C.L.W, ldw = D.ldw;
+    FCtx C = f_make_ctx<kCoop>(D, qp, Lfac, Wfac, Kfac, sF);
     const int t = FV(F_PT), d = FV(F_D), hW = FV(F_HW), aug = FV(F_AUG), w = FV(F_W), t0 = FV(F_T0),
               t1 = FV(F_T1), rsv = FV(F_S), c2 = FV(F_RV), dxt = FV(F_RXT), dxo = FV(F_XT);
     _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[t1 + i] = rx_in[(int64_t)qp * n + i];
@@ -1327,12 +1111,17 @@ k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ 
     }
     __syncthreads();
     f_whiten(C.L.Lp, n, FV(F_DINVL), t1, t);                    // t = L^-1 rx
-    f_matvec_rows1(W, ldw, ms, n, t, c2);
+    if (kCoop) {
+        __syncthreads();
+        f_issue_K(D, C);
+    }
+    mv_rows1<kCoop>(D, C, t, c2);
     __syncthreads();
     _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) qsm[aug + i] = -(qsm[c2 + i] + qsm[hW + i]);
     __syncthreads();
     f_factor_and_solve(D, C, false);                                   // w = [dy; dz]
-    f_matvec_cols(W, ldw, ms, n, w, t0, t1, dxt, t, -1.0, -1, -1.0);
+    mv_cols<kCoop>(D, C, w, t0, t1, dxt, t, -1.0, -1, -1.0);
+    if (kCoop) f_stage_L(D, C);                                 // (mv_cols ended with a block barrier; no K copy in flight)
     f_unwhiten(C.L.Lp, n, FV(F_DINVL), dxt, dxo);               // dx = L^-T dx~
     _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) dx_out[(int64_t)qp * n + i] = qsm[dxo + i];
     _Pragma("unroll 1") for (int i = tid; i < m; i += kNT) {
@@ -1661,7 +1450,8 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
     const int64_t solve_mat = (int64_t)plan->rows_s * plan->lds;     // global mode: only the S workspace
     const int64_t solve_vec = (int64_t)solve_vec_doubles(plan->vl);
     KDims D = dims_of(plan);
-    const int64_t fast_doubles = (int64_t)fk::fast_smem_doubles(D);
+    const int64_t fast_doubles = (int64_t)fk::fast_smem_doubles(D, false);
+    const int64_t coop_doubles = (int64_t)fk::fast_smem_doubles(D, true);
     const bool setup_fits = (setup_mat + setup_vec) * 8 <= kMaxSmem;
     const bool fast_ok = setup_fits && fast_doubles * 8 <= kMaxSmem && nineq <= 8 * kCholMaxTiles && (msp - plan->neq_pad) / 8 >= 1 && msp <= 224;
     const bool fits = setup_fits && (solve_mat_s + solve_vec) * 8 <= kMaxSmem;
@@ -1669,6 +1459,11 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
     const bool setup_fast_ok = fast_ok && nz <= 8 * kCholMaxTiles && (int64_t)SL.total * 8 <= kMaxSmem;
     plan->fast = fast_ok ? 1 : 0;
     plan->setup_fast = setup_fast_ok ? 1 : 0;
+    // co-resident mode: two CTAs per SM (each needs its share of the 227 KB plus the 1 KB the hardware reserves per
+    // CTA), the packed L must fit the S workspace it visits, W rows must be 16-byte aligned (ld is even by construction)
+    plan->coop_smem_bytes = coop_doubles * 8;
+    plan->coop_ok = (fast_ok && coop_doubles * 8 <= (232448 / 2 - 1024 - 64) && plan->L_elems <= (int64_t)msp * plan->lds) ? 1 : 0;
+    plan->coop = plan->coop_ok ? kCoopDefault : 0;
     plan->smem_resident = (fast_ok || fits) ? 1 : 0;
     if (setup_fits && (fast_ok || fits)) {
         plan->setup_smem_bytes = setup_fast_ok ? (int64_t)SL.total * 8 : (setup_mat + setup_vec) * 8;
@@ -1733,10 +1528,16 @@ int qpb200_forward(const qpb200_plan* plan, int nbatch, const double* p, int64_t
             D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim,     \
             maxIter, zhat, lam, slacks, nus, iters, best_resid, trace, SCR, SCRN);                      \
     } while (0)
-    if (plan->fast) {
-        int rc = set_smem(k_forward_fast, plan->solve_smem_bytes);
+    if (plan->fast && plan->coop && plan->coop_ok) {
+        int rc = set_smem(k_forward_fast<true>, plan->coop_smem_bytes);
         if (rc) return rc;
-        k_forward_fast<<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
+        k_forward_fast<true><<<nbatch, kThreads, plan->coop_smem_bytes, st>>>(
+            D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, maxIter,
+            zhat, lam, slacks, nus, iters, best_resid, trace);
+    } else if (plan->fast) {
+        int rc = set_smem(k_forward_fast<false>, plan->solve_smem_bytes);
+        if (rc) return rc;
+        k_forward_fast<false><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
             D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, maxIter,
             zhat, lam, slacks, nus, iters, best_resid, trace);
     } else if (plan->smem_resident) {
@@ -1769,10 +1570,15 @@ int qpb200_solve_kkt(const qpb200_plan* plan, int nbatch, const double* d, const
             D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz, \
             dy, O, SCR, SCRN);                                                                          \
     } while (0)
-    if (plan->fast) {
-        int rc = set_smem(k_kkt_fast<false>, plan->solve_smem_bytes);
+    if (plan->fast && plan->coop && plan->coop_ok) {
+        int rc = set_smem(k_kkt_fast<false, true>, plan->coop_smem_bytes);
         if (rc) return rc;
-        k_kkt_fast<false><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
+        k_kkt_fast<false, true><<<nbatch, kThreads, plan->coop_smem_bytes, st>>>(
+            D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz, dy, O);
+    } else if (plan->fast) {
+        int rc = set_smem(k_kkt_fast<false, false>, plan->solve_smem_bytes);
+        if (rc) return rc;
+        k_kkt_fast<false, false><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
             D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz, dy, O);
     } else if (plan->smem_resident) {
         QPB_LAUNCH_KKT(true, false, nullptr, 0);
@@ -1809,10 +1615,16 @@ int qpb200_backward(const qpb200_plan* plan, int nbatch, const double* dl_dzhat,
             D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac,  \
             sF, dxv, nullptr, dlamv, dnuv, O, SCR, SCRN);                                               \
     } while (0)
-    if (plan->fast) {
-        int rc = set_smem(k_kkt_fast<true>, plan->solve_smem_bytes);
+    if (plan->fast && plan->coop && plan->coop_ok) {
+        int rc = set_smem(k_kkt_fast<true, true>, plan->coop_smem_bytes);
         if (rc) return rc;
-        k_kkt_fast<true><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
+        k_kkt_fast<true, true><<<nbatch, kThreads, plan->coop_smem_bytes, st>>>(
+            D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac, sF, dxv,
+            nullptr, dlamv, dnuv, O);
+    } else if (plan->fast) {
+        int rc = set_smem(k_kkt_fast<true, false>, plan->solve_smem_bytes);
+        if (rc) return rc;
+        k_kkt_fast<true, false><<<nbatch, kThreads, plan->solve_smem_bytes, st>>>(
             D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac, sF, dxv,
             nullptr, dlamv, dnuv, O);
     } else if (plan->smem_resident) {
