@@ -5,7 +5,7 @@ hold the reference's outputs for exactly these inputs plus an input checksum.
 """
 import numpy as np
 
-from qpth_b200.problems import random_qp_batch, cls_layer_problem
+from qpth_b200.problems import random_qp_batch, cls_layer_problem, c5_shard
 
 
 def checksum(prob):
@@ -92,12 +92,6 @@ def sweep_problem(i):
     b = np.einsum("ben,bn->be", A, z0)
     dl = rs.randn(B, n)
     return dict(Q=Q, p=p, G=G, h=h, A=A, b=b, dl=dl)
-
-
-def c5_shard(rank, per_rank=1024):
-    """Shard `rank` of BASELINE.json config 5 (B=8192, nz=nineq=100 over 8 ranks): every shard is rebuilt from its
-    own seed, so no rank (and no test) ever materialises the 1.3 GB global batch."""
-    return random_qp_batch(per_rank, 100, 100, 0, seed=5000 + rank)
 
 
 def _testpy(tag_kw):

@@ -90,5 +90,7 @@ def plan_for(nz, nineq, neq):
         p = Plan()
         rc = load().qpb200_plan_init(nz, nineq, neq, ctypes.byref(p))
         check(rc)
+        if os.environ.get("QPB200_COOP") is not None and p.coop_ok:     # development knob: force a kernel family
+            p.coop = 1 if os.environ["QPB200_COOP"] == "1" else 0
         _plans[key] = p
     return _plans[key]

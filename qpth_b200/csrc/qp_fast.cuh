@@ -20,6 +20,11 @@ namespace fast {
 // Optional cycle accounting (build with -DQPB_TIMING): thread 0 of block 0 accumulates clock64() deltas per
 // phase into g_tim[]; read back with qpb200_debug_timing(). Compiled out of the product build.
 #ifdef QPB_TIMING
+// per-CTA record of k_forward_fast: {globaltimer at entry, at exit (ns), Newton iterations, SM id}
+__device__ long long g_cta[4 * 8192];
+__device__ int g_tim_target = 0;          // which QP's phase slots are exported (qpb200_debug_timing(., 2 + qp))
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ int smid() { int r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 __device__ long long g_tim[128];
 // accumulators live in (static) shared memory so that a tick costs ~40 cycles, not a global round trip
 __shared__ long long s_tim[129];

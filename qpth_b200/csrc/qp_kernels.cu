@@ -853,7 +853,11 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     const int qp = blockIdx.x;
     const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
 #ifdef QPB_TIMING
-    if (threadIdx.x == 0) { for (int i = 0; i < 128; ++i) s_tim[i] = 0; s_tim[128] = clock64(); s_tim2 = s_tim[128]; }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 128; ++i) s_tim[i] = 0;
+        s_tim[128] = clock64(); s_tim2 = s_tim[128];
+        if (qp < 8192) { g_cta[4 * qp] = gtimer(); g_cta[4 * qp + 3] = smid(); }
+    }
     __syncthreads();
 #endif
     FCtx C = f_make_ctx<kCoop>(D, qp, Lfac, Wfac, Kfac, sF);
@@ -1067,7 +1071,9 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         resid_out[qp] = ret_resid;
     }
 #ifdef QPB_TIMING
-    if (tid == 0 && qp == 0) for (int i = 0; i < 128; ++i) g_tim[i] = s_tim[i];
+    QPB_TICK(16);
+    if (tid == 0 && qp == g_tim_target) for (int i = 0; i < 128; ++i) g_tim[i] = s_tim[i];
+    if (tid == 0 && qp < 8192) { g_cta[4 * qp + 1] = gtimer(); g_cta[4 * qp + 2] = iters_run; }
 #endif
 }
 
@@ -1653,12 +1659,18 @@ int qpb200_backward(const qpb200_plan* plan, int nbatch, const double* dl_dzhat,
 
 #ifdef QPB_TIMING
 int qpb200_debug_timing(long long* host64, int reset) {
-    if (reset) {
+    if (reset) {                          // 1: clear the slots; 2 + qp: clear and export QP `qp`'s slots from now on
         long long z[128] = {0};
         CK(cudaMemcpyToSymbol(qpb::fast::g_tim, z, sizeof(z)));
+        const int target = reset >= 2 ? reset - 2 : 0;
+        CK(cudaMemcpyToSymbol(qpb::fast::g_tim_target, &target, sizeof(int)));
         return QPB200_OK;
     }
     CK(cudaMemcpyFromSymbol(host64, qpb::fast::g_tim, 128 * sizeof(long long)));
+    return QPB200_OK;
+}
+int qpb200_debug_cta(long long* host64, int nqp) {    // {t0_ns, t1_ns, iters, smid} per QP of the last forward launch
+    CK(cudaMemcpyFromSymbol(host64, qpb::fast::g_cta, (size_t)4 * nqp * sizeof(long long)));
     return QPB200_OK;
 }
 #endif

@@ -89,3 +89,62 @@ def sharded_qp(solve, Q, p, G, h, A, b, nbatch, src=0, group=None, device=None):
     e = torch.Tensor()
     z = solve(*[x if x is not None else e for x in parts])
     return gather_batch(z.detach(), nbatch, dst=src, group=group)
+
+
+def _scatter_even(out, full, src, group):
+    """dist.scatter of equal contiguous shards (NCCL and gloo both implement it); `full` only on `src`."""
+    ws, rk = dist.get_world_size(group), dist.get_rank(group)
+    chunks = list(full.chunk(ws, dim=0)) if rk == src else None
+    dist.scatter(out, scatter_list=chunks, src=src, group=group)
+
+
+def _gather_even(shard, full, dst, group):
+    ws, rk = dist.get_world_size(group), dist.get_rank(group)
+    chunks = list(full.chunk(ws, dim=0)) if rk == dst else None
+    dist.gather(shard, gather_list=chunks, dst=dst, group=group)
+
+
+def sharded_qp_timed(f, glob, nbatch, nz, nineq, device, include_comm=True, src=0, group=None, dl=None):
+    """BASELINE.json config 5 as one job: rank `src` holds the fully batched Q, p, G, h (dict `glob`, None elsewhere);
+    they are scattered (NCCL scatter over NVLink; equal shards - ragged batches go through `sharded_qp`), every rank
+    runs `f` forward + backward on its shard, z* is gathered on `src`; the per-sample gradients stay on the rank that
+    produced them (gathering 1.3 GB of dQ/dG is the one thing a data-parallel consumer never needs).
+    Returns dict(ms = device time of the region, max over ranks; z = gathered z* on `src`; grads = local gradients).
+    include_comm=False times the solve alone (scatter before the first event, gather after the second)."""
+    ws, rk = dist.get_world_size(group), dist.get_rank(group)
+    assert nbatch % ws == 0, "sharded_qp_timed needs equal shards (use sharded_qp for ragged batches)"
+    nloc = nbatch // ws
+    f64 = dict(dtype=torch.float64, device=device)
+    shapes = {"Q": (nz, nz), "p": (nz,), "G": (nineq, nz), "h": (nineq,)}
+    loc = {k: torch.empty((nloc,) + shp, **f64) for k, shp in shapes.items()}
+    zfull = torch.empty(nbatch, nz, **f64) if rk == src else None
+    e = torch.empty(0, **f64)
+    if dl is None:
+        dl = torch.ones(nloc, nz, **f64)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def scatter():
+        for k in ("Q", "p", "G", "h"):
+            _scatter_even(loc[k], glob[k] if rk == src else None, src, group)
+
+    if include_comm:
+        ev0.record()
+        scatter()
+    else:
+        scatter()
+        torch.cuda.synchronize()
+        ev0.record()
+    t = {k: v.requires_grad_(True) for k, v in loc.items()}
+    z = f(t["Q"], t["p"], t["G"], t["h"], e, e)
+    z.backward(dl)
+    zd = z.detach().contiguous()
+    if include_comm:
+        _gather_even(zd, zfull, src, group)
+        ev1.record()
+    else:
+        ev1.record()
+        _gather_even(zd, zfull, src, group)
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], **f64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=group)
+    return dict(ms=float(ms.item()), z=zfull, grads={k: v.grad for k, v in t.items()}, nloc=nloc)

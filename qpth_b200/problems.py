@@ -60,6 +60,12 @@ def cls_layer_problem(nBatch, nz, nineq, seed=0):
     return dict(Q=Q, p=p, G=G, h=h, A=np.zeros((0, nz)), b=np.zeros((0,)), dl=dl)
 
 
+def c5_shard(rank, per_rank=1024):
+    """Shard `rank` of BASELINE.json config 5 (B = 8192, nz = nineq = 100, eight shards of 1024): every shard is
+    rebuilt from its own seed, so no rank (and no test) has to materialise the 1.3 GB global batch to check one."""
+    return random_qp_batch(per_rank, 100, 100, 0, seed=5000 + rank)
+
+
 def algorithmic_bytes_per_qp(nz, nineq, neq, itemsize=8):
     """compulsory HBM bytes per QP for fwd+bwd, all inputs batched."""
     n, m, e = nz, nineq, neq
