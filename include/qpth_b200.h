@@ -61,6 +61,8 @@ typedef struct qpb200_plan {
                              *    from L2 instead of being staged in shared memory)                                  */
     int coop;               /* 1: use them (plan_init's default when coop_ok; the caller may clear it to get the
                              *    one-QP-per-SM kernels, which have the lower latency for a batch smaller than the GPU) */
+    int tiny;               /* 1: nz, ms_pad <= 32: one WARP per QP (32-thread CTAs, up to 16 QPs per SM) with the generic
+                             *    shared-memory kernels; `threads` is then 32                                        */
 } qpb200_plan;
 
 int qpb200_version(void);

@@ -24,7 +24,7 @@ class Plan(ctypes.Structure):
         ("L_elems", ctypes.c_int64), ("W_elems", ctypes.c_int64), ("K_elems", ctypes.c_int64),
         ("setup_scratch_elems", ctypes.c_int64), ("solve_scratch_elems", ctypes.c_int64),
         ("setup_smem_bytes", ctypes.c_int64), ("solve_smem_bytes", ctypes.c_int64),
-        ("coop_smem_bytes", ctypes.c_int64), ("coop_ok", ctypes.c_int), ("coop", ctypes.c_int),
+        ("coop_smem_bytes", ctypes.c_int64), ("coop_ok", ctypes.c_int), ("coop", ctypes.c_int), ("tiny", ctypes.c_int),
     ]
 
 

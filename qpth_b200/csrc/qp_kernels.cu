@@ -18,6 +18,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/qpth_b200.h"
 #include "qp_device.cuh"
 #include "qp_fast.cuh"
@@ -27,10 +29,17 @@ using namespace qpb;
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kTinyThreads = 32;        // tiny problems: one warp per QP (generic shared-memory kernels, 32-thread CTAs)
+constexpr int kTinyCtasPerSm = 16;
+constexpr int kTinyMax = 32;            // nz and ms_pad up to this size take the one-warp-per-QP path
 #ifndef QPB_COOP_DEFAULT
 #define QPB_COOP_DEFAULT 1     // plan_init selects the co-resident kernels whenever the shape allows (plan->coop)
 #endif
 constexpr int kCoopDefault = QPB_COOP_DEFAULT;
+#ifndef QPB_TINY_DEFAULT
+#define QPB_TINY_DEFAULT 1
+#endif
+constexpr int kTinyDefault = QPB_TINY_DEFAULT;
 constexpr int kMaxSmem = 232448 - 1024;   // 227 KB opt-in limit per CTA on sm_100, minus static smem slack
 
 struct KDims {
@@ -91,8 +100,10 @@ __device__ __forceinline__ void finish_dxt(const double* W, int ldw, int ms, int
 // ---------------------------------------------------------------------------------------------
 // k_setup: pre_factor_kkt. One CTA per (Q,G,A) system.
 // ---------------------------------------------------------------------------------------------
-template <bool kSmem>
-__global__ void __launch_bounds__(kThreads, 1)
+// kTiny: the same kernel launched with ONE WARP per system (plan->tiny: nz, ms <= 32), up to 16 systems per SM; every
+// __syncthreads() is then a single-warp barrier and the rows-per-thread loops make one pass.
+template <bool kSmem, bool kTiny = false>
+__global__ void __launch_bounds__(kTiny ? kTinyThreads : kThreads, kTiny ? kTinyCtasPerSm : 1)
 k_setup(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __restrict__ G, int64_t sG,
         const double* __restrict__ A, int64_t sA, double* __restrict__ Lfac,
         double* __restrict__ Wfac, double* __restrict__ Kfac, int* __restrict__ spd_flag,
@@ -332,8 +343,8 @@ __device__ __forceinline__ void load_dinvs(const KDims& D, const Ctx& C, int tid
 // ---------------------------------------------------------------------------------------------
 // k_forward: the PDIPM loop (batch.py:47-207), per-QP semantics.
 // ---------------------------------------------------------------------------------------------
-template <bool kSmem, bool kV2>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kSmem, bool kV2, bool kTiny = false>
+__global__ void __launch_bounds__(kTiny ? kTinyThreads : kThreads, kTiny ? kTinyCtasPerSm : 1)
 k_forward(KDims D, const double* __restrict__ p, int64_t sp, const double* __restrict__ h,
           int64_t sh, const double* __restrict__ b, int64_t sb, const double* __restrict__ Lfac,
           const double* __restrict__ Wfac, const double* __restrict__ Kfac, int sF, double eps,
@@ -548,8 +559,8 @@ struct BwdOut {
     int mQ, mp, mG, mh, mA, mb;      // 1 = mean-reduced elsewhere (skip per-QP write)
 };
 
-template <bool kSmem, bool kV2, bool kBackward>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kSmem, bool kV2, bool kBackward, bool kTiny = false>
+__global__ void __launch_bounds__(kTiny ? kTinyThreads : kThreads, kTiny ? kTinyCtasPerSm : 1)
 k_solve_kkt(KDims D, const double* __restrict__ d_in, const double* __restrict__ rx_in,
             const double* __restrict__ rs_in, const double* __restrict__ rz_in,
             const double* __restrict__ ry_in, const double* __restrict__ zhat,
@@ -1390,15 +1401,19 @@ KDims dims_of(const qpb200_plan* p) {
 
 // cudaFuncSetAttribute is not free (and may serialise with the driver): raise the dynamic shared-memory
 // limit of a kernel only when it has to grow. Keyed by (device, kernel).
+// The table is shared by every host thread that calls into the library (ctypes releases the GIL: the autograd engine
+// thread runs backward while user threads run forward, one thread per GPU in multi-device processes), hence the lock.
 struct SmemSet { const void* fn; int dev; size_t bytes; };
 SmemSet g_smem_set[64];
 int g_smem_n = 0;
+std::mutex g_smem_mu;
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
     int dev = 0;
     CK(cudaGetDevice(&dev));
     const void* fn = reinterpret_cast<const void*>(kernel);
+    std::lock_guard<std::mutex> lock(g_smem_mu);
     for (int i = 0; i < g_smem_n; ++i)
         if (g_smem_set[i].fn == fn && g_smem_set[i].dev == dev) {
             if (g_smem_set[i].bytes >= bytes) return QPB200_OK;
@@ -1463,6 +1478,18 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
     const bool fits = setup_fits && (solve_mat_s + solve_vec) * 8 <= kMaxSmem;
     const fk::SLayout SL = fk::setup_layout(D);
     const bool setup_fast_ok = fast_ok && nz <= 8 * kCholMaxTiles && (int64_t)SL.total * 8 <= kMaxSmem;
+    // tiny problems (the sizes of the reference's own tests and prof scripts, test.py:99-187 nz = 10): a 256-thread
+    // CTA per QP is 8 warps synchronising over a handful of rows; one warp per QP and 16 QPs per SM instead
+    const bool tiny = kTinyDefault && fits && nz <= kTinyMax && msp <= kTinyMax;
+    plan->tiny = tiny ? 1 : 0;
+    if (tiny) {
+        plan->fast = 0; plan->setup_fast = 0; plan->smem_resident = 1; plan->threads = kTinyThreads;
+        plan->setup_smem_bytes = (setup_mat + setup_vec) * 8;
+        plan->solve_smem_bytes = (solve_mat_s + solve_vec) * 8;
+        plan->setup_scratch_elems = 0; plan->solve_scratch_elems = 0;
+        plan->coop_smem_bytes = 0; plan->coop_ok = 0; plan->coop = 0;
+        return QPB200_OK;
+    }
     plan->fast = fast_ok ? 1 : 0;
     plan->setup_fast = setup_fast_ok ? 1 : 0;
     // co-resident mode: two CTAs per SM (each needs its share of the 227 KB plus the 1 KB the hardware reserves per
@@ -1494,7 +1521,12 @@ int qpb200_pre_factor_kkt(const qpb200_plan* plan, int nsys, const double* Q, in
     if (plan->neq > 0 && !A) return QPB200_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     KDims D = dims_of(plan);
-    if (plan->setup_fast) {
+    if (plan->tiny) {
+        int rc = set_smem(k_setup<true, true>, plan->setup_smem_bytes);
+        if (rc) return rc;
+        k_setup<true, true><<<nsys, kTinyThreads, plan->setup_smem_bytes, st>>>(D, Q, sQ, G, sG, A, sA, Lfac, Wfac, Kfac,
+                                                                                 spd_flag, nullptr, 0);
+    } else if (plan->setup_fast) {
         int rc = set_smem(k_setup_fast, plan->setup_smem_bytes);
         if (rc) return rc;
         k_setup_fast<<<nsys, kThreads, plan->setup_smem_bytes, st>>>(D, Q, sQ, G, sG, A, sA, Lfac, Wfac, Kfac, spd_flag);
@@ -1534,7 +1566,13 @@ int qpb200_forward(const qpb200_plan* plan, int nbatch, const double* p, int64_t
             D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim,     \
             maxIter, zhat, lam, slacks, nus, iters, best_resid, trace, SCR, SCRN);                      \
     } while (0)
-    if (plan->fast && plan->coop && plan->coop_ok) {
+    if (plan->tiny) {
+        int rc = set_smem(k_forward<true, false, true>, plan->solve_smem_bytes);
+        if (rc) return rc;
+        k_forward<true, false, true><<<nbatch, kTinyThreads, plan->solve_smem_bytes, st>>>(
+            D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, maxIter, zhat, lam,
+            slacks, nus, iters, best_resid, trace, nullptr, 0);
+    } else if (plan->fast && plan->coop && plan->coop_ok) {
         int rc = set_smem(k_forward_fast<true>, plan->coop_smem_bytes);
         if (rc) return rc;
         k_forward_fast<true><<<nbatch, kThreads, plan->coop_smem_bytes, st>>>(
@@ -1576,7 +1614,12 @@ int qpb200_solve_kkt(const qpb200_plan* plan, int nbatch, const double* d, const
             D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz, \
             dy, O, SCR, SCRN);                                                                          \
     } while (0)
-    if (plan->fast && plan->coop && plan->coop_ok) {
+    if (plan->tiny) {
+        int rc = set_smem(k_solve_kkt<true, false, false, true>, plan->solve_smem_bytes);
+        if (rc) return rc;
+        k_solve_kkt<true, false, false, true><<<nbatch, kTinyThreads, plan->solve_smem_bytes, st>>>(
+            D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz, dy, O, nullptr, 0);
+    } else if (plan->fast && plan->coop && plan->coop_ok) {
         int rc = set_smem(k_kkt_fast<false, true>, plan->coop_smem_bytes);
         if (rc) return rc;
         k_kkt_fast<false, true><<<nbatch, kThreads, plan->coop_smem_bytes, st>>>(
@@ -1621,7 +1664,13 @@ int qpb200_backward(const qpb200_plan* plan, int nbatch, const double* dl_dzhat,
             D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac,  \
             sF, dxv, nullptr, dlamv, dnuv, O, SCR, SCRN);                                               \
     } while (0)
-    if (plan->fast && plan->coop && plan->coop_ok) {
+    if (plan->tiny) {
+        int rc = set_smem(k_solve_kkt<true, false, true, true>, plan->solve_smem_bytes);
+        if (rc) return rc;
+        k_solve_kkt<true, false, true, true><<<nbatch, kTinyThreads, plan->solve_smem_bytes, st>>>(
+            D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac, sF, dxv, nullptr,
+            dlamv, dnuv, O, nullptr, 0);
+    } else if (plan->fast && plan->coop && plan->coop_ok) {
         int rc = set_smem(k_kkt_fast<true, true>, plan->coop_smem_bytes);
         if (rc) return rc;
         k_kkt_fast<true, true><<<nbatch, kThreads, plan->coop_smem_bytes, st>>>(
@@ -1682,6 +1731,20 @@ int qpb200_dfma_probe(int blocks, int threads, int iters, double* out, void* str
     return QPB200_OK;
 }
 
+// Device resources of one qpb200_qp_host call: released on every exit path.
+namespace {
+struct HostCallGuard {
+    cudaStream_t st = nullptr;
+    double* arena = nullptr;
+    int* iarena = nullptr;
+    ~HostCallGuard() {
+        if (arena) cudaFree(arena);
+        if (iarena) cudaFree(iarena);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+}  // namespace
+
 int qpb200_qp_host(int device, int nbatch, int nz, int nineq, int neq, const double* Q_host,
                    const double* p_host, const double* G_host, const double* h_host,
                    const double* A_host, const double* b_host, const double* dl_host, double eps,
@@ -1692,9 +1755,12 @@ int qpb200_qp_host(int device, int nbatch, int nz, int nineq, int neq, const dou
     int rc = qpb200_plan_init(nz, nineq, neq, &P);
     if (rc) return rc;
     if (nbatch <= 0 || !Q_host || !p_host || !zhat_host) return QPB200_ERR_BAD_ARG;
+    if (nineq <= 0 || !G_host || !h_host) return QPB200_ERR_BAD_ARG;      // (equality-only problems: not supported, as in QPFunction)
+    if (neq > 0 && (!A_host || !b_host)) return QPB200_ERR_BAD_ARG;
     CK(cudaSetDevice(device));
-    cudaStream_t st;
-    CK(cudaStreamCreate(&st));
+    HostCallGuard R;
+    CK(cudaStreamCreate(&R.st));
+    cudaStream_t st = R.st;
     const int64_t B = nbatch, n = nz, m = nineq, e = neq;
     const bool bwd = dl_host != nullptr;
     // one arena: inputs | factors | outputs | work
@@ -1704,11 +1770,9 @@ int qpb200_qp_host(int device, int nbatch, int nz, int nineq, int neq, const dou
     const int64_t ngrad = bwd ? B * (n * n + n + m * n + m + e * n + e + n + m + e) : 0;
     const int64_t nscr = B * (P.solve_scratch_elems > P.setup_scratch_elems ? P.solve_scratch_elems
                                                                              : P.setup_scratch_elems);
-    double* arena = nullptr;
-    int* iarena = nullptr;
-    CK(cudaMalloc(&arena, (size_t)(nin + nfac + nout + ngrad + nscr + 8) * sizeof(double)));
-    CK(cudaMalloc(&iarena, (size_t)(2 * B) * sizeof(int)));
-    double* q = arena;
+    CK(cudaMalloc(&R.arena, (size_t)(nin + nfac + nout + ngrad + nscr + 8) * sizeof(double)));
+    CK(cudaMalloc(&R.iarena, (size_t)(2 * B) * sizeof(int)));
+    double* q = R.arena;
     double* dQm = q; q += B * n * n;
     double* dpv = q; q += B * n;
     double* dGm = q; q += B * m * n;
@@ -1731,8 +1795,8 @@ int qpb200_qp_host(int device, int nbatch, int nz, int nineq, int neq, const dou
         gA = q; q += B * e * n; gb = q; q += B * e; wx = q; q += B * n; wl = q; q += B * m; wn = q; q += B * e;
     }
     double* scr = nscr ? q : nullptr;
-    int* dflag = iarena;
-    int* diters = iarena + B;
+    int* dflag = R.iarena;
+    int* diters = R.iarena + B;
 #define H2D(dst, src, cnt) if ((cnt) > 0) CK(cudaMemcpyAsync(dst, src, (size_t)(cnt) * sizeof(double), cudaMemcpyHostToDevice, st))
 #define D2H(dst, src, cnt) if ((cnt) > 0 && (dst)) CK(cudaMemcpyAsync(dst, src, (size_t)(cnt) * sizeof(double), cudaMemcpyDeviceToHost, st))
     H2D(dQm, Q_host, B * n * n); H2D(dpv, p_host, B * n); H2D(dGm, G_host, B * m * n);
@@ -1754,14 +1818,12 @@ int qpb200_qp_host(int device, int nbatch, int nz, int nineq, int neq, const dou
         }
         if (spd_flag_host)
             CK(cudaMemcpyAsync(spd_flag_host, dflag, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
-        cudaError_t err = cudaStreamSynchronize(st);
-        if (err != cudaSuccess) rc = cuda_fail(err, "cudaStreamSynchronize");
     }
+    // the stream is drained on every path before the guard frees what the queued work uses
+    cudaError_t err = cudaStreamSynchronize(st);
+    if (!rc && err != cudaSuccess) rc = cuda_fail(err, "cudaStreamSynchronize");
 #undef H2D
 #undef D2H
-    cudaFree(arena);
-    cudaFree(iarena);
-    cudaStreamDestroy(st);
     return rc;
 }
 

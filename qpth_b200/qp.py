@@ -24,7 +24,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from .util import expandParam, extract_nBatch
+from .util import check_shapes, expandParam, extract_nBatch
 
 INACC_ERR = """
 --------
@@ -84,25 +84,19 @@ class _Solved:
 def solve_forward(Q_, p_, G_, h_, A_, b_, eps=1e-12, verbose=0, notImprovedLim=3, maxIter=20,
                   check_Q_spd=True):
     """pre_factor_kkt + forward on the device. Inputs follow QPFunction's conventions. Returns _Solved."""
+    # rank errors exactly as expandParam raises them (util.py:44-50), then every trailing dimension / batch size:
+    # pure host logic, done before anything touches the device
+    nBatch, nz, nineq, neq = check_shapes(Q_, p_, G_, h_, A_, b_)
+    assert neq > 0 or nineq > 0                         # qp.py:89
+    if nineq == 0:
+        raise RuntimeError('qpth_b200: nineq == 0 is not supported (the reference unpacks G.size() at qp.py:87)')
+    assert maxIter >= 1
     lib = _lib.load()
     if not torch.cuda.is_available():
         raise _lib.QpthB200Error("qpth_b200: no CUDA device available (there is no CPU fallback).")
-    nBatch = extract_nBatch(Q_, p_, G_, h_, A_, b_)
-    # shape checks exactly as expandParam would raise them (util.py:44-50)
-    for X, nd in ((Q_, 3), (p_, 2), (G_, 3), (h_, 2), (A_, 3), (b_, 2)):
-        expandParam(X, nBatch, nd)
     device = Q_.device if Q_.is_cuda else torch.device("cuda", torch.cuda.current_device())
     with torch.cuda.device(device):
         Q, p, G, h = (_dev64(t, device) for t in (Q_, p_, G_, h_))
-        neq = 0
-        if A_.nelement() > 0:
-            neq = A_.size(-2)
-        nineq = G.size(-2) if G.nelement() > 0 else 0
-        nz = Q.size(-1)
-        assert neq > 0 or nineq > 0                     # qp.py:89
-        if nineq == 0:
-            raise RuntimeError('qpth_b200: nineq == 0 is not supported (the reference unpacks G.size() at qp.py:87)')
-        assert maxIter >= 1
         A = _dev64(A_, device) if neq > 0 else None
         b = _dev64(b_, device) if neq > 0 else None
         plan = _lib.plan_for(nz, nineq, neq)

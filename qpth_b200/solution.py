@@ -31,21 +31,17 @@ from .util import expandParam, extract_nBatch
 def pre_factor_state(Q_, p_, G_, h_, A_, b_, zhat, lams, slacks, nus, check_Q_spd=True):
     """`pre_factor_kkt` on the device + the given solution, packaged as the state `solve_backward` consumes."""
     from .qp import _Solved, _dev64, _ptr, _stream
+    from .util import check_shapes
+    nBatch, nz, nineq, neq = check_shapes(Q_, p_, G_, h_, A_, b_)
+    assert neq > 0 or nineq > 0                         # qp.py:89
+    if nineq == 0:
+        raise RuntimeError('qpth_b200: nineq == 0 is not supported (the reference unpacks G.size() at qp.py:87)')
     lib = _lib.load()
     if not torch.cuda.is_available():
         raise _lib.QpthB200Error("qpth_b200: no CUDA device available (there is no CPU fallback).")
-    nBatch = extract_nBatch(Q_, p_, G_, h_, A_, b_)
-    for X, nd in ((Q_, 3), (p_, 2), (G_, 3), (h_, 2), (A_, 3), (b_, 2)):
-        expandParam(X, nBatch, nd)
     device = Q_.device if Q_.is_cuda else torch.device("cuda", torch.cuda.current_device())
     with torch.cuda.device(device):
         Q, G = _dev64(Q_, device), _dev64(G_, device)
-        neq = A_.size(-2) if A_.nelement() > 0 else 0
-        nineq = G.size(-2) if G.nelement() > 0 else 0
-        nz = Q.size(-1)
-        assert neq > 0 or nineq > 0                     # qp.py:89
-        if nineq == 0:
-            raise RuntimeError('qpth_b200: nineq == 0 is not supported (the reference unpacks G.size() at qp.py:87)')
         A = _dev64(A_, device) if neq > 0 else None
         plan = _lib.plan_for(nz, nineq, neq)
         sQ = nz * nz if Q.dim() == 3 else 0

@@ -29,6 +29,42 @@ def expandParam(X, nBatch, nDim):
     return X.unsqueeze(0).expand(nBatch, *X.shape), True
 
 
+def check_shapes(Q, p, G, h, A, b):
+    """Validate every trailing dimension and batch size BEFORE raw pointers and strides go to the kernels.
+
+    The reference gets these errors for free from `bmm` / `expand` (a torch shape RuntimeError somewhere inside
+    `pre_factor_kkt` or `forward`); here nothing downstream would notice - the kernels would read out of bounds.
+    Returns (nBatch, nz, nineq, neq). Rank errors are `expandParam`'s ("Unexpected number of dimensions.").
+    """
+    nBatch = extract_nBatch(Q, p, G, h, A, b)
+    for X, nd in zip((Q, p, G, h, A, b), _PARAM_RANKS):
+        expandParam(X, nBatch, nd)
+
+    def fail(msg):
+        raise RuntimeError("qpth_b200: inconsistent shapes: " + msg)
+
+    if Q.nelement() == 0 or Q.dim() < 2:
+        fail("Q must be (nBatch, nz, nz) or (nz, nz), got %s" % (tuple(Q.shape),))
+    nz = int(Q.size(-1))
+    if Q.size(-2) != nz:
+        fail("Q is not square: %s" % (tuple(Q.shape),))
+    nineq = int(G.size(-2)) if (G.nelement() > 0 and G.dim() >= 2) else 0
+    neq = int(A.size(-2)) if (A.nelement() > 0 and A.dim() >= 2) else 0
+    want = (("p", p, (nz,), True), ("G", G, (nineq, nz), nineq > 0), ("h", h, (nineq,), nineq > 0),
+            ("A", A, (neq, nz), neq > 0), ("b", b, (neq,), neq > 0))
+    for name, X, trail, needed in want:
+        if not needed:
+            if X.nelement() != 0:
+                fail("%s given %s but its constraint block is empty" % (name, tuple(X.shape)))
+            continue
+        if X.nelement() == 0 or tuple(X.shape[-len(trail):]) != trail:
+            fail("%s has shape %s, expected trailing dimensions %s" % (name, tuple(X.shape), trail))
+    for name, X, rank in zip("QpGhAb", (Q, p, G, h, A, b), _PARAM_RANKS):
+        if X.nelement() > 0 and X.dim() == rank and X.size(0) != nBatch:
+            fail("%s has batch size %d, the batch is %d" % (name, X.size(0), nBatch))
+    return nBatch, nz, nineq, neq
+
+
 def get_sizes(G, A=None):
     """(nineq, nz, neq, nBatch) from G (2-D or 3-D) and optionally A; neq is None when A is not given (util.py:22-33)."""
     if G.dim() not in (2, 3):

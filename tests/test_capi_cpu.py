@@ -41,6 +41,17 @@ def test_plan_shapes(lib):
     assert (p.neq_pad, p.ms) == (16, 66)
     p = _lib.plan_for(200, 200, 0)
     assert p.smem_resident == 0 and p.solve_scratch_elems > 0
+    # kernel-family selection (include/qpth_b200.h): co-resident fast kernels at C2/C3, one warp per QP for tiny shapes
+    p = _lib.plan_for(100, 100, 0)
+    assert (p.fast, p.coop_ok, p.tiny, p.threads) == (1, 1, 0, 256) and 2 * (p.coop_smem_bytes + 1024) <= 232448
+    p = _lib.plan_for(10, 5, 0)
+    assert (p.tiny, p.threads, p.fast, p.smem_resident, p.coop) == (1, 32, 0, 1, 0) and 16 * p.solve_smem_bytes <= 232448
+    p = _lib.plan_for(32, 24, 8)
+    assert p.tiny == 1
+    p = _lib.plan_for(33, 10, 0)
+    assert p.tiny == 0
+    p = _lib.plan_for(150, 20, 0)          # chol(Q) does not fit the S workspace it would have to visit
+    assert (p.fast, p.setup_fast, p.coop_ok) == (1, 0, 0)
     bad = _lib.Plan()
     assert lib.qpb200_plan_init(5, 0, 0, ctypes.byref(bad)) == 2      # QPB200_ERR_NO_CONSTRAINTS
     assert lib.qpb200_plan_init(0, 3, 0, ctypes.byref(bad)) == 1
@@ -114,3 +125,38 @@ def test_util_helpers_behave_like_qpth_util():
         a, b = U.expandParam(X, 3, nd), R.expandParam(X, 3, nd)
         assert a[1] == b[1] and a[0].shape == b[0].shape and a[0].stride() == b[0].stride()
     assert U.get_sizes(G, A) == R.get_sizes(G, A) and torch.equal(U.bdiag(x), R.bdiag(x))
+
+
+def test_shape_validation_raises_before_the_device_is_touched():
+    """mismatched trailing dimensions / batch sizes must raise, not reach the kernels (CPU-only check:
+    the validation runs before the library or a CUDA device is needed)."""
+    import pytest
+    import torch
+    from qpth_b200 import QPFunction
+    from qpth_b200.util import check_shapes
+    B, n, m, e = 3, 5, 4, 2
+    d = torch.float64
+    Q, p = torch.eye(n, dtype=d).repeat(B, 1, 1), torch.zeros(B, n, dtype=d)
+    G, h = torch.ones(B, m, n, dtype=d), torch.ones(B, m, dtype=d)
+    A, b = torch.ones(B, e, n, dtype=d), torch.ones(B, e, dtype=d)
+    E = torch.Tensor()
+    assert check_shapes(Q, p, G, h, A, b) == (B, n, m, e)
+    assert check_shapes(Q[0], p, G[0], h[0], E, E) == (B, n, m, 0)
+    bad = [
+        (Q, p[:, :-1], G, h, A, b),                 # p.size(-1) != nz
+        (Q, p, G[:, :, :-1], h, A, b),              # G.size(-1) != nz
+        (Q, p, G, h[:, :-1], A, b),                 # h.size(-1) != nineq
+        (Q, p, G, h, A[:, :, :-1], b),              # A.size(-1) != nz
+        (Q, p, G, h, A, b[:, :-1]),                 # b.size(-1) != neq
+        (Q[:, :, :-1], p, G, h, A, b),              # Q not square
+        (Q, p[:2], G, h, A, b),                     # batch sizes disagree
+        (Q, p, G.new_ones(1, m, n), h, A, b),       # G batched over 1, Q over B
+        (Q, p, G, h, E, b),                         # b without A
+    ]
+    for args in bad:
+        with pytest.raises(RuntimeError, match="inconsistent shapes"):
+            check_shapes(*args)
+        with pytest.raises(RuntimeError, match="inconsistent shapes"):
+            QPFunction(verbose=-1)(*args)
+    with pytest.raises(RuntimeError, match="Unexpected number of dimensions."):
+        QPFunction(verbose=-1)(Q[None], p, G, h, A, b)

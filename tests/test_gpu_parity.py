@@ -48,8 +48,9 @@ def _run(prob, requires=True, **opts):
 
 SWEEP = [c for c in CASES if c.startswith("sweep")]
 # which kernel family a case must exercise: (fast, setup_fast, smem_resident); None = do not care
+EXPECTED_TINY = ("c1", "eq_small", "ineq_only_wide", "shared", "unbatched", "testpy_dp", "testpy_dG", "testpy_dA")
 EXPECTED_PATH = {
-    "c2": (1, 1, 1), "c3": (1, 1, 1), "c5_shard0": (1, 1, 1), "c1": (1, 1, 1),
+    "c2": (1, 1, 1), "c3": (1, 1, 1), "c5_shard0": (1, 1, 1), "c3_b64": (1, 1, 1), "c4_small": (1, 1, 1),
     "band_smem": (0, 0, 1), "band_smem_eq": (0, 0, 1),           # nineq > 104: generic shared-memory kernels
     "band_setup": (1, 0, 1), "band_setup_eq": (1, 0, 1),         # nz > 104: fast solve kernels, generic setup
     "c4": (0, 0, 0),                                             # 200 x 200: global-scratch kernels
@@ -80,6 +81,11 @@ def test_matches_reference_golden(name, golden_dir):
         plan = _lib.plan_for(np.asarray(prob["Q"]).shape[-1], np.asarray(prob["G"]).shape[-2],
                              np.asarray(prob["A"]).shape[-2] if np.asarray(prob["A"]).size else 0)
         assert (plan.fast, plan.setup_fast, plan.smem_resident) == EXPECTED_PATH[name], name
+        assert plan.tiny == 0
+    if name in EXPECTED_TINY:       # one warp per QP (nz, ms_pad <= 32): the sizes of the reference's own tests
+        Qs, Gs, As = np.asarray(prob["Q"]), np.asarray(prob["G"]), np.asarray(prob["A"])
+        plan = _lib.plan_for(Qs.shape[-1], Gs.shape[-2], As.shape[-2] if As.size else 0)
+        assert plan.tiny == 1 and plan.threads == 32, name
 
 
 @pytest.mark.parametrize("name", SWEEP)
