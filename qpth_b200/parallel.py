@@ -121,7 +121,22 @@ def sharded_qp_timed(f, glob, nbatch, nz, nineq, device, include_comm=True, src=
     e = torch.empty(0, **f64)
     if dl is None:
         dl = torch.ones(nloc, nz, **f64)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    on_gpu = torch.device(device).type == "cuda"
+
+    class _HostClock:       # gloo / CPU tests: same protocol as a CUDA event, wall clock
+        def record(self):
+            import time
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+
+    ev0, ev1 = ((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if on_gpu
+                else (_HostClock(), _HostClock()))
+
+    def sync():
+        if on_gpu:
+            torch.cuda.synchronize()
 
     def scatter():
         for k in ("Q", "p", "G", "h"):
@@ -132,7 +147,7 @@ def sharded_qp_timed(f, glob, nbatch, nz, nineq, device, include_comm=True, src=
         scatter()
     else:
         scatter()
-        torch.cuda.synchronize()
+        sync()
         ev0.record()
     t = {k: v.requires_grad_(True) for k, v in loc.items()}
     z = f(t["Q"], t["p"], t["G"], t["h"], e, e)
@@ -144,7 +159,7 @@ def sharded_qp_timed(f, glob, nbatch, nz, nineq, device, include_comm=True, src=
     else:
         ev1.record()
         _gather_even(zd, zfull, src, group)
-    torch.cuda.synchronize()
+    sync()
     ms = torch.tensor([ev0.elapsed_time(ev1)], **f64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX, group=group)
     return dict(ms=float(ms.item()), z=zfull, grads={k: v.grad for k, v in t.items()}, nloc=nloc)

@@ -58,3 +58,38 @@ def test_shard_bounds_cover_batch():
             b = [shard_bounds(n, w, r) for r in range(w)]
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+
+
+def _worker_c5(rank, world, port, results):
+    """The config-5 job function (scatter -> fwd+bwd on the shard -> gather z*) under gloo with an injected
+    differentiable CPU solver: exercises exactly the collectives bench.py runs over NCCL."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from qpth_b200 import parallel
+        from qpth_b200.problems import random_qp_batch
+        nbatch, nz, nineq = 8, 6, 4
+        pr = random_qp_batch(nbatch, nz, nineq, 0, seed=3)
+        glob = {k: torch.from_numpy(pr[k]) for k in ("Q", "p", "G", "h")} if rank == 0 else None
+
+        def f(Q, p, G, h, A, b):          # stand-in with the layer's signature: unconstrained minimiser -Q^-1 p
+            return -torch.linalg.solve(Q, p.unsqueeze(-1)).squeeze(-1) + 0.0 * (G.sum((1, 2)) + h.sum(1)).unsqueeze(-1)
+
+        for comm in (True, False):
+            out = parallel.sharded_qp_timed(f, glob, nbatch, nz, nineq, torch.device("cpu"), include_comm=comm)
+            assert out["ms"] >= 0.0 and out["nloc"] == nbatch // world
+            assert tuple(out["grads"]["Q"].shape) == (nbatch // world, nz, nz)
+            if rank == 0:
+                ref = -np.linalg.solve(pr["Q"], pr["p"][:, :, None])[:, :, 0]
+                results["zerr_%d" % comm] = float(np.abs(out["z"].numpy() - ref).max())
+            else:
+                assert out["z"] is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_c5_job_function_world2():
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker_c5, args=(2, _free_port(), results), nprocs=2, join=True)
+    assert results["zerr_1"] < 1e-9 and results["zerr_0"] < 1e-9     # (Q is ill-conditioned: two LAPACK paths)
