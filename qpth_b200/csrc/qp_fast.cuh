@@ -467,7 +467,7 @@ __device__ __noinline__ void f_trsv_bwd(int A, int ld, int n, int u, int w) {
 // Storage: X_k's strictly lower part TRANSPOSED in the (otherwise unused) upper triangle of its diagonal block,
 // X_k[i][j] (i > j) at M[(k0 + j) * ld + k0 + i]; its diagonal is the reciprocal diagonal already there.
 #ifndef QPB_TRSV16
-#define QPB_TRSV16 1
+#define QPB_TRSV16 0     // measured (profiles/r2_experiments.md): 21.6k cycles for inversion + three solves vs 16.9k with the 8-row chain
 #endif
 
 // All 16 x 16 diagonal blocks of the factored n x n matrix at A (n multiple of 8, n <= 256). One half-warp per

@@ -33,7 +33,8 @@ constexpr int kTinyThreads = 32;        // tiny problems: one warp per QP (gener
 constexpr int kTinyCtasPerSm = 16;
 constexpr int kTinyMax = 32;            // nz and ms_pad up to this size take the one-warp-per-QP path
 #ifndef QPB_COOP_DEFAULT
-#define QPB_COOP_DEFAULT 1     // plan_init selects the co-resident kernels whenever the shape allows (plan->coop)
+#define QPB_COOP_DEFAULT 0     // measured (profiles/r2_experiments.md): the co-resident kernels LOSE (128-register cap spills
+                               // the register-resident Cholesky, L2 passes cost 3x the shared-memory ones); opt-in only
 #endif
 constexpr int kCoopDefault = QPB_COOP_DEFAULT;
 #ifndef QPB_TINY_DEFAULT
@@ -650,18 +651,52 @@ k_solve_kkt(KDims D, const double* __restrict__ d_in, const double* __restrict__
     }
 }
 
-// Batch-mean gradients for un-batched inputs (qp.py:159-177): out[r][c] = (1/B) sum_b (u_b[r] x_b[c] + y_b[r] v_b[c]) * scale
-__global__ void k_mean_outer(int B, int rows, int cols, const double* __restrict__ u,
-                             const double* __restrict__ x, const double* __restrict__ y,
-                             const double* __restrict__ v, double scale, double* __restrict__ out) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * cols) return;
-    const int r = idx / cols, c = idx - r * cols;
-    double s = 0.0;
-    for (int bidx = 0; bidx < B; ++bidx)
-        s += u[(int64_t)bidx * rows + r] * x[(int64_t)bidx * cols + c] +
-             y[(int64_t)bidx * rows + r] * v[(int64_t)bidx * cols + c];
-    out[idx] = s * scale / (double)B;
+// Batch-mean gradients for un-batched inputs (qp.py:159-177):
+//   out[r][c] = scale / B * sum_b (u_b[r] x_b[c] + y_b[r] v_b[c])     i.e.  scale / B * (U^T X + Y^T V),
+// a (rows x B)(B x cols) product computed straight from the per-QP vectors (no B x rows x cols round trip).
+// One CTA per 32 x 64 output tile: the batch is walked in chunks of 16 QPs staged in shared memory with loads that are
+// contiguous in the vector index, every thread owns a 2 x 4 register tile (8 outputs, 16 FMAs per staged b).
+constexpr int kMoR = 32, kMoC = 64, kMoB = 16;
+__global__ void __launch_bounds__(256)
+k_mean_outer(int B, int rows, int cols, const double* __restrict__ u, const double* __restrict__ x,
+             const double* __restrict__ y, const double* __restrict__ v, double scale, double* __restrict__ out) {
+    __shared__ double su[kMoB][kMoR], sy[kMoB][kMoR], sx[kMoB][kMoC], sv[kMoB][kMoC];
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.y * kMoR, c0 = blockIdx.x * kMoC;
+    const int tr = (tid >> 4) * 2, tc = (tid & 15) * 4;           // 16 x 16 threads, 2 x 4 outputs each
+    double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+    for (int b0 = 0; b0 < B; b0 += kMoB) {
+        for (int i = tid; i < kMoB * kMoR; i += 256) {
+            const int bb = i / kMoR, rr = i - bb * kMoR;
+            const bool ok = (b0 + bb < B) && (r0 + rr < rows);
+            su[bb][rr] = ok ? u[(int64_t)(b0 + bb) * rows + r0 + rr] : 0.0;
+            sy[bb][rr] = ok ? y[(int64_t)(b0 + bb) * rows + r0 + rr] : 0.0;
+        }
+        for (int i = tid; i < kMoB * kMoC; i += 256) {
+            const int bb = i / kMoC, cc = i - bb * kMoC;
+            const bool ok = (b0 + bb < B) && (c0 + cc < cols);
+            sx[bb][cc] = ok ? x[(int64_t)(b0 + bb) * cols + c0 + cc] : 0.0;
+            sv[bb][cc] = ok ? v[(int64_t)(b0 + bb) * cols + c0 + cc] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int bb = 0; bb < kMoB; ++bb) {
+            const double u0 = su[bb][tr], u1 = su[bb][tr + 1], y0 = sy[bb][tr], y1 = sy[bb][tr + 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double xj = sx[bb][tc + j], vj = sv[bb][tc + j];
+                acc[0][j] = fma(u0, xj, fma(y0, vj, acc[0][j]));
+                acc[1][j] = fma(u1, xj, fma(y1, vj, acc[1][j]));
+            }
+        }
+        __syncthreads();
+    }
+    const double sc = scale / (double)B;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (r0 + tr + i < rows && c0 + tc + j < cols) out[(int64_t)(r0 + tr + i) * cols + c0 + tc + j] = acc[i][j] * sc;
 }
 __global__ void k_mean_vec(int B, int len, const double* __restrict__ u, double scale,
                            double* __restrict__ out) {
@@ -1692,14 +1727,14 @@ int qpb200_backward(const qpb200_plan* plan, int nbatch, const double* dl_dzhat,
     CK(cudaGetLastError());
     const int TB = 256;
     if (dQ && mean_Q)
-        k_mean_outer<<<(n * n + TB - 1) / TB, TB, 0, st>>>(nbatch, n, n, dxv, zhat, zhat, dxv, 0.5, dQ);
+        k_mean_outer<<<dim3((n + kMoC - 1) / kMoC, (n + kMoR - 1) / kMoR), 256, 0, st>>>(nbatch, n, n, dxv, zhat, zhat, dxv, 0.5, dQ);
     if (dp && mean_p) k_mean_vec<<<(n + TB - 1) / TB, TB, 0, st>>>(nbatch, n, dxv, 1.0, dp);
     if (dG && mean_G)
-        k_mean_outer<<<(m * n + TB - 1) / TB, TB, 0, st>>>(nbatch, m, n, dlamv, zhat, lam, dxv, 1.0, dG);
+        k_mean_outer<<<dim3((n + kMoC - 1) / kMoC, (m + kMoR - 1) / kMoR), 256, 0, st>>>(nbatch, m, n, dlamv, zhat, lam, dxv, 1.0, dG);
     if (dh && mean_h) k_mean_vec<<<(m + TB - 1) / TB, TB, 0, st>>>(nbatch, m, dlamv, -1.0, dh);
     if (e > 0) {
         if (dA && mean_A)
-            k_mean_outer<<<(e * n + TB - 1) / TB, TB, 0, st>>>(nbatch, e, n, dnuv, zhat, nus, dxv, 1.0, dA);
+            k_mean_outer<<<dim3((n + kMoC - 1) / kMoC, (e + kMoR - 1) / kMoR), 256, 0, st>>>(nbatch, e, n, dnuv, zhat, nus, dxv, 1.0, dA);
         if (db && mean_b) k_mean_vec<<<(e + TB - 1) / TB, TB, 0, st>>>(nbatch, e, dnuv, -1.0, db);
     }
     CK(cudaGetLastError());
