@@ -63,6 +63,12 @@ typedef struct qpb200_plan {
                              *    one-QP-per-SM kernels, which have the lower latency for a batch smaller than the GPU) */
     int tiny;               /* 1: nz, ms_pad <= 32: one WARP per QP (32-thread CTAs, up to 16 QPs per SM) with the generic
                              *    shared-memory kernels; `threads` is then 32                                        */
+    int pf;                 /* 1: product-form kernels: factor_kkt produces T_k = L_kk^-1 and P_ik = L_ik T_k directly (fp64
+                             *    tensor pipe), substitutions are chain-free, K and the factor use the staircase layout
+                             *    (K_elems = 32 t^2 + 64 t doubles, t = ms_pad / 8). Decided by plan_init; do not toggle.   */
+    int pf_global;          /* with pf: 1 = W and chol(Q) are read from global memory (large problems, e.g. nz = nineq =
+                             *    200: factor + vectors fill the shared memory), 0 = staged in shared memory             */
+    int64_t pf_smem_bytes;  /* dynamic shared memory of the product-form solve kernels */
 } qpb200_plan;
 
 int qpb200_version(void);

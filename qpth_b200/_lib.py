@@ -25,6 +25,7 @@ class Plan(ctypes.Structure):
         ("setup_scratch_elems", ctypes.c_int64), ("solve_scratch_elems", ctypes.c_int64),
         ("setup_smem_bytes", ctypes.c_int64), ("solve_smem_bytes", ctypes.c_int64),
         ("coop_smem_bytes", ctypes.c_int64), ("coop_ok", ctypes.c_int), ("coop", ctypes.c_int), ("tiny", ctypes.c_int),
+        ("pf", ctypes.c_int), ("pf_global", ctypes.c_int), ("pf_smem_bytes", ctypes.c_int64),
     ]
 
 
@@ -85,7 +86,8 @@ _plans = {}
 
 
 def plan_for(nz, nineq, neq):
-    key = (nz, nineq, neq)
+    # QPB200_PF (development / A-B knob read by qpb200_plan_init: "0" never, "1" product-form kernels wherever they fit)
+    key = (nz, nineq, neq, os.environ.get("QPB200_PF"))
     if key not in _plans:
         p = Plan()
         rc = load().qpb200_plan_init(nz, nineq, neq, ctypes.byref(p))

@@ -421,7 +421,10 @@ __device__ __forceinline__ void load_T8(const double* A, int ld, int k0, int nb,
 }
 
 // tab[idx] = (ti << 8) | tj for the off-diagonal tiles (ti > tj) enumerated column by column.
+// The table holds 96 entries (kTabDoubles): orders above 13 tile rows never use it (generic kernels, chol_partial) and
+// must not write it (r2b: compute-sanitizer caught the overflow at ms = 128).
 __device__ __forceinline__ void build_tile_table(uint16_t* tab, int nts, int tid) {
+    if (nts > kCholMaxTiles) return;
     if (tid < nts - 1) {
         const int tj = tid;
         const int base = tj * (nts - 1) - (tj * (tj - 1)) / 2;

@@ -16,6 +16,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -23,6 +24,7 @@
 #include "../../include/qpth_b200.h"
 #include "qp_device.cuh"
 #include "qp_fast.cuh"
+#include "qp_pf.cuh"
 
 using namespace qpb;
 
@@ -41,6 +43,10 @@ constexpr int kCoopDefault = QPB_COOP_DEFAULT;
 #define QPB_TINY_DEFAULT 1
 #endif
 constexpr int kTinyDefault = QPB_TINY_DEFAULT;
+#ifndef QPB_PF_DEFAULT
+#define QPB_PF_DEFAULT 0       // product-form kernels: 0 = only for shapes without a fast kernel, 1 = wherever they fit
+#endif
+constexpr int kPfDefault = QPB_PF_DEFAULT;
 constexpr int kMaxSmem = 232448 - 1024;   // 227 KB opt-in limit per CTA on sm_100, minus static smem slack
 
 struct KDims {
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(kTiny ? kTinyThreads : kThreads, kTiny ? kTiny
 k_setup(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __restrict__ G, int64_t sG,
         const double* __restrict__ A, int64_t sA, double* __restrict__ Lfac,
         double* __restrict__ Wfac, double* __restrict__ Kfac, int* __restrict__ spd_flag,
-        double* __restrict__ gscratch, int64_t scratch_per_sys) {
+        double* __restrict__ gscratch, int64_t scratch_per_sys, int pf) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int sys = blockIdx.x;
@@ -139,7 +145,8 @@ k_setup(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __restr
 
     double* Lg = Lfac + (int64_t)sys * D.lp;                 // packed lower
     double* Wg = Wfac + (int64_t)sys * ms * D.ldw;           // row stride ldw (= the SMEM layout)
-    double* Kg = Kfac + (int64_t)sys * D.msp * D.lds;        // msp rows, row stride lds (= the SMEM layout)
+    // msp rows, row stride lds (= the SMEM layout), or the staircase of the product-form kernels (qp_pf.cuh)
+    double* Kg = Kfac + (int64_t)sys * (pf ? qpb::pf::pf_elems(D.msp >> 3) : D.msp * D.lds);
     for (int i = tid; i < n * n; i += nt) {
         const int r = i / n, c = i - r * n;
         if (c <= r) Lg[(r * (r + 1)) / 2 + c] = RA[r * ldn + c];
@@ -188,6 +195,11 @@ k_setup(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __restr
     // storage convention: the diagonal of the pre-factored equality columns holds 1 / L_cc
     for (int i = tid; i < ep; i += nt) RA[i * ldk + i] = 1.0 / RA[i * ldk + i];
     __syncthreads();
+    if (pf) {                                                   // equality columns -> product form, K -> staircase
+        qpb::pf::pf_convert_cols(RA, ldk, ms, ep >> 3, tid, nt);
+        qpb::pf::pf_write_staircase(Kg, RA, ldk, ms, D.msp, tid, nt);
+        return;
+    }
     for (int i = tid; i < D.msp * D.lds; i += nt) {             // msp rows: identity-padded to a multiple of 8
         const int r = i / D.lds, c = i - r * D.lds;
         Kg[i] = (r < ms) ? ((c < ms) ? RA[r * ldk + c] : 0.0) : (r == c ? 1.0 : 0.0);
@@ -717,26 +729,33 @@ enum FVec { F_PT = 0, F_XT, F_RXT, F_S, F_V, F_RV, F_HW, F_W, F_DSA, F_DS, F_D, 
             F_DINV, F_DINVL, F_AUG, F_T0, F_T1, F_COUNT };
 
 struct FLayout {              // offsets in doubles into the dynamic shared array
-    int W, LS, Lp, vec, red, bar, tab;
+    int W, LS, Lp, vec, red, bar, tab, pan;
     int vl;
 };
 __host__ __device__ inline int fast_vl(int n, int msp) { return ((n > msp ? n : msp) + 7) & ~7; }
-// coop = co-resident mode: W and packed L are NOT staged (they are read from global memory, qp_fast.cuh); the
-// packed L visits the S workspace twice (whitening at entry, un-whitening at exit), so Lp aliases LS.
-__host__ __device__ inline FLayout fast_layout(const KDims& D, bool coop) {
+// coop = W and packed L are NOT staged (they are read from global memory, qp_fast.cuh). Without pf the packed L
+// visits the S workspace twice (whitening at entry, un-whitening at exit), so Lp aliases LS; with pf the two packed-L
+// substitutions read L straight from global memory and nothing is staged.
+// pf = product-form factor in the staircase layout (qp_pf.cuh): S shrinks to pf_elems, plus the panel scratch.
+__host__ __device__ inline int s_doubles(const KDims& D, bool pf) {
+    return pf ? qpb::pf::pf_elems(D.msp >> 3) : D.msp * D.lds;
+}
+__host__ __device__ inline FLayout fast_layout(const KDims& D, bool coop, bool pf = false) {
     FLayout L;
     L.vl = fast_vl(D.n, D.msp);
     L.W = 0;
     L.LS = coop ? 0 : L.W + D.ms * D.ldw;
-    L.Lp = coop ? L.LS : L.LS + D.msp * D.lds;
-    L.vec = coop ? L.LS + D.msp * D.lds : L.Lp + D.lp;
+    L.pan = L.LS + s_doubles(D, pf);
+    const int after_s = L.pan + (pf ? D.msp * qpb::pf::kPanLd : 0);
+    L.Lp = coop ? L.LS : after_s;
+    L.vec = coop ? after_s : L.Lp + D.lp;
     L.red = L.vec + F_COUNT * L.vl;
     L.bar = L.red + kRedDoubles;
     L.tab = L.bar + 2;
     return L;
 }
-__host__ __device__ inline size_t fast_smem_doubles(const KDims& D, bool coop) {
-    const FLayout L = fast_layout(D, coop);
+__host__ __device__ inline size_t fast_smem_doubles(const KDims& D, bool coop, bool pf = false) {
+    const FLayout L = fast_layout(D, coop, pf);
     return (size_t)L.tab + kTabDoubles;
 }
 
@@ -747,6 +766,7 @@ struct FCtx {
     const double* Lg;
     uint32_t kphase;
     uint32_t lphase;      // parity of the next completion on bar[0] (W/L staging)
+    uint32_t kbytes;      // size of the K template (square or staircase layout)
     bool kpending;
 };
 #define FV(i) (C.L.vec + (i) * C.L.vl)
@@ -760,7 +780,7 @@ __device__ __noinline__ void f_issue_K_impl(int LS, const double* Kg, int bar_of
 }
 // Call with all threads AFTER a block barrier that retired every reader of the previous factor.
 __device__ __forceinline__ void f_issue_K(const KDims& D, FCtx& C) {
-    if (threadIdx.x == 0) f_issue_K_impl(C.L.LS, C.Kg, C.L.bar, (uint32_t)(D.msp * D.lds * 8));
+    if (threadIdx.x == 0) f_issue_K_impl(C.L.LS, C.Kg, C.L.bar, C.kbytes);
     C.kpending = true;
 }
 __device__ __forceinline__ void f_wait_K(FCtx& C) {
@@ -788,16 +808,17 @@ __device__ __forceinline__ void f_stage_L(const KDims& D, FCtx& C) {
 // Stage W and packed L with TMA, start the first K copy, build the tile table.
 // kCoop: only L is staged (into the S workspace, for the whitening of the caller's first vector); the caller issues
 // the first K copy itself once it is done with L (f_issue_K after a block barrier).
-template <bool kCoop>
+template <bool kCoop, bool kPF = false>
 __device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double* Lfac, const double* Wfac,
                                            const double* Kfac, int sF) {
     QPB_SMEM;
     FCtx C;
-    C.L = fast_layout(D, kCoop);
+    C.L = fast_layout(D, kCoop, kPF);
     const int64_t sys = sF ? qp : 0;
+    C.kbytes = (uint32_t)(s_doubles(D, kPF) * 8);
     C.Lg = Lfac + sys * (int64_t)D.lp;
     C.Wg = Wfac + sys * (int64_t)D.ms * D.ldw;
-    C.Kg = Kfac + sys * (int64_t)D.msp * D.lds;
+    C.Kg = Kfac + sys * (int64_t)s_doubles(D, kPF);
     C.kphase = 0;
     C.lphase = 0;
     C.kpending = false;
@@ -807,8 +828,13 @@ __device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double*
         mbar_init(bar, 1);
         mbar_init(bar + 1, 1);
     }
-    build_tile_table(reinterpret_cast<uint16_t*>(qsm + C.L.tab), (D.msp - D.ep) >> 3, tid);
+    if (!kPF) build_tile_table(reinterpret_cast<uint16_t*>(qsm + C.L.tab), (D.msp - D.ep) >> 3, tid);
     __syncthreads();
+    if (kCoop && kPF) {
+        f_issue_K(D, C);                                         // nothing is staged: L is read from global memory
+        _Pragma("unroll 1") for (int i = tid; i < D.n; i += kNT) qsm[FV(F_DINVL) + i] = 1.0 / C.Lg[(i * (i + 1)) / 2 + i];
+        return C;
+    }
     if (kCoop) {
         f_stage_L(D, C);
     } else {
@@ -824,6 +850,20 @@ __device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double*
     // reciprocal diagonals of L (packed) and of the pre-factored equality block
     _Pragma("unroll 1") for (int i = tid; i < D.n; i += kNT) qsm[FV(F_DINVL) + i] = 1.0 / qsm[C.L.Lp + (i * (i + 1)) / 2 + i];
     return C;
+}
+
+// x~ = L^-1 x and x = L^-T x~ with the packed L in shared memory, or (global W/L + product form) straight from global
+template <bool kGlobalL>
+__device__ __forceinline__ void f_whiten_x(const KDims& D, const FCtx& C, int b, int u) {
+    QPB_SMEM;
+    if (kGlobalL) trsv_fwd(C.Lg, PackedIdx{}, D.n, 0, D.n, qsm + FV(F_DINVL), qsm + b, qsm + u, (int)threadIdx.x, kNT);
+    else f_whiten(C.L.Lp, D.n, FV(F_DINVL), b, u);
+}
+template <bool kGlobalL>
+__device__ __forceinline__ void f_unwhiten_x(const KDims& D, const FCtx& C, int u, int w) {
+    QPB_SMEM;
+    if (kGlobalL) trsv_bwd(C.Lg, PackedIdx{}, D.n, qsm + FV(F_DINVL), qsm + u, qsm + w, (int)threadIdx.x, kNT);
+    else f_unwhiten(C.L.Lp, D.n, FV(F_DINVL), u, w);
 }
 
 // mat-vec dispatch: shared-memory resident W / L, or the global-memory passes of the co-resident mode
@@ -879,13 +919,31 @@ __device__ __forceinline__ void f_factor_and_solve(const KDims& D, FCtx& C, bool
     QPB_TICK(33);   // backward substitution
 }
 
+// The same with the product-form factor (qp_pf.cuh): F_AUG = -h_full, F_D = d  ->  F_W = -S^-1 h_full; F_T0 scratch.
+__device__ __forceinline__ void f_factor_and_solve_pf(const KDims& D, FCtx& C) {
+    QPB_SMEM;
+    using namespace qpb::pf;
+    const int tid = threadIdx.x;
+    f_wait_K(C);
+    _Pragma("unroll 1") for (int i = D.ep + tid; i < D.ms; i += kNT) qsm[C.L.LS + pf_rowoff(i) + i] += 1.0 / qsm[FV(F_D) + i];
+    __syncthreads();
+    if (D.ep > 0) pf_fwd(C.L.LS, D.msp, 0, D.ep >> 3, FV(F_AUG));
+    pf_chol(C.L.LS, D.msp >> 3, D.ep >> 3, FV(F_AUG), C.L.pan);
+    QPB_TICK(32);
+    pf_diag(C.L.LS, D.msp, FV(F_AUG), FV(F_T0), FV(F_AUG));
+    pf_bwd(C.L.LS, D.msp, FV(F_AUG), FV(F_W));
+    QPB_TICK(33);
+}
+
 __device__ __forceinline__ double f_step_fix(double v) { return (isinf(v) && v > 0.0) ? 1.0 : v; }
 
 }  // namespace fk
 
 // kCoop: co-resident mode (two CTAs per SM; W and L read from global memory, see qp_fast.cuh).
-template <bool kCoop>
-__global__ void __launch_bounds__(kThreads, kCoop ? 2 : 1)
+// kPF: product-form factor in the staircase layout (qp_pf.cuh); with kCoop it is the "large problem" kernel: factor
+// and vectors in shared memory, W and L read from global memory (L2-resident when the system is shared), ONE CTA per SM.
+template <bool kCoop, bool kPF = false>
+__global__ void __launch_bounds__(kThreads, (kCoop && !kPF) ? 2 : 1)
 k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* __restrict__ h, int64_t sh,
                const double* __restrict__ b, int64_t sb, const double* __restrict__ Lfac,
                const double* __restrict__ Wfac, const double* __restrict__ Kfac, int sF, double eps,
@@ -906,7 +964,8 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     }
     __syncthreads();
 #endif
-    FCtx C = f_make_ctx<kCoop>(D, qp, Lfac, Wfac, Kfac, sF);
+    FCtx C = f_make_ctx<kCoop, kPF>(D, qp, Lfac, Wfac, Kfac, sF);
+    constexpr bool kGL = kCoop && kPF;                          // packed L read from global memory, nothing staged
     QPB_TICK(0);
     const int pt = FV(F_PT), xt = FV(F_XT), rxt = FV(F_RXT), s = FV(F_S), v = FV(F_V), rv = FV(F_RV),
               hW = FV(F_HW), w = FV(F_W), dsa = FV(F_DSA), ds = FV(F_DS), d = FV(F_D), hb = FV(F_HB),
@@ -929,8 +988,8 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     }
     __syncthreads();
     QPB_TICK(1);
-    f_whiten(C.L.Lp, n, FV(F_DINVL), t1, pt);                   // p~ = L^-1 p
-    if (kCoop) {                                                // L leaves the S workspace: the first K copy may land
+    f_whiten_x<kGL>(D, C, t1, pt);                              // p~ = L^-1 p
+    if (kCoop && !kPF) {                                        // L leaves the S workspace: the first K copy may land
         __syncthreads();
         f_issue_K(D, C);
     }
@@ -941,7 +1000,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     __syncthreads();
     _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) qsm[aug + i] = -(qsm[hW + i] + qsm[hb + i]);
     __syncthreads();
-    f_factor_and_solve(D, C, false);
+    if (kPF) f_factor_and_solve_pf(D, C); else f_factor_and_solve(D, C, false);
     f_issue_K(D, C);
     mv_cols<kCoop>(D, C, w, t0, t1, xt, pt, -1.0, -1, -1.0);   // x~ = -p~ - W^T w
     {
@@ -1015,7 +1074,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         }
         __syncthreads();
         QPB_TICK(9);
-        f_factor_and_solve(D, C, true);                               // w = [dy_aff; dz_aff]
+        if (kPF) f_factor_and_solve_pf(D, C); else f_factor_and_solve(D, C, true);   // w = [dy_aff; dz_aff]
         QPB_TICK(10);
         // ---- affine step length and sigma (batch.py:160-168)
         double mn[2] = {INFINITY, INFINITY};
@@ -1050,6 +1109,11 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
             __syncthreads();
         }
         QPB_TICK(11);
+        int wc = t1;                                             // where [dy_cor; dz_cor] lands
+        if (kPF) {
+            qpb::pf::pf_solve(C.L.LS, msp, t1, t0, hW);         // (hW is dead until the combined direction below)
+            wc = hW;
+        } else {
 #if QPB_PFORM
         f_ptrsv_fwd(C.L.LS, D.lds, msp, t1, t0);
         QPB_TICK(12);
@@ -1063,12 +1127,13 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         QPB_TICK(12);
         f_trsv_bwd(C.L.LS, D.lds, msp, t0, t1);                  // t1 = [dy_cor; dz_cor]
 #endif
+        }
         QPB_TICK(13);
         f_issue_K(D, C);                                         // next factor_kkt's K copy overlaps the rest
         // ---- combined direction, step length, update (batch.py:185-203)
         mn[0] = INFINITY; mn[1] = INFINITY;
         _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) {
-            const double wci = qsm[t1 + i];
+            const double wci = qsm[wc + i];
             const double dv = qsm[w + i] + wci;
             qsm[w + i] = dv;
             if (i >= ep) {
@@ -1098,12 +1163,12 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     // ---- outputs: x = L^-T x~_best, y, z, s of the returned iterate (batch.py:205-207)
     __syncthreads();
     QPB_TICK(16);
-    if (kCoop) {                                                 // the S workspace is dead: L comes back for x = L^-T x~
+    if (kCoop && !kPF) {                                         // the S workspace is dead: L comes back for x = L^-T x~
         if (C.kpending) f_wait_K(C);
         __syncthreads();
         f_stage_L(D, C);
     }
-    f_unwhiten(C.L.Lp, n, FV(F_DINVL), FV(F_BXT), t0);
+    f_unwhiten_x<kGL>(D, C, FV(F_BXT), t0);
     if (C.kpending) f_wait_K(C);                                 // drain the in-flight copy before exit
     _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) zhat[(int64_t)qp * n + i] = qsm[t0 + i];
     _Pragma("unroll 1") for (int i = tid; i < m; i += kNT) {
@@ -1123,8 +1188,8 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
 #endif
 }
 
-template <bool kBackward, bool kCoop>
-__global__ void __launch_bounds__(kThreads, kCoop ? 2 : 1)
+template <bool kBackward, bool kCoop, bool kPF = false>
+__global__ void __launch_bounds__(kThreads, (kCoop && !kPF) ? 2 : 1)
 k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ rx_in,
            const double* __restrict__ rs_in, const double* __restrict__ rz_in,
            const double* __restrict__ ry_in, const double* __restrict__ zhat,
@@ -1138,7 +1203,8 @@ k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ 
     const int tid = threadIdx.x;
     const int qp = blockIdx.x;
     const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
-    FCtx C = f_make_ctx<kCoop>(D, qp, Lfac, Wfac, Kfac, sF);
+    FCtx C = f_make_ctx<kCoop, kPF>(D, qp, Lfac, Wfac, Kfac, sF);
+    constexpr bool kGL = kCoop && kPF;
     const int t = FV(F_PT), d = FV(F_D), hW = FV(F_HW), aug = FV(F_AUG), w = FV(F_W), t0 = FV(F_T0),
               t1 = FV(F_T1), rsv = FV(F_S), c2 = FV(F_RV), dxt = FV(F_RXT), dxo = FV(F_XT);
     _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[t1 + i] = rx_in[(int64_t)qp * n + i];
@@ -1162,8 +1228,8 @@ k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ 
         qsm[aug + i] = 0.0;
     }
     __syncthreads();
-    f_whiten(C.L.Lp, n, FV(F_DINVL), t1, t);                    // t = L^-1 rx
-    if (kCoop) {
+    f_whiten_x<kGL>(D, C, t1, t);                               // t = L^-1 rx
+    if (kCoop && !kPF) {
         __syncthreads();
         f_issue_K(D, C);
     }
@@ -1171,10 +1237,10 @@ k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ 
     __syncthreads();
     _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) qsm[aug + i] = -(qsm[c2 + i] + qsm[hW + i]);
     __syncthreads();
-    f_factor_and_solve(D, C, false);                                   // w = [dy; dz]
+    if (kPF) f_factor_and_solve_pf(D, C); else f_factor_and_solve(D, C, false);   // w = [dy; dz]
     mv_cols<kCoop>(D, C, w, t0, t1, dxt, t, -1.0, -1, -1.0);
-    if (kCoop) f_stage_L(D, C);                                 // (mv_cols ended with a block barrier; no K copy in flight)
-    f_unwhiten(C.L.Lp, n, FV(F_DINVL), dxt, dxo);               // dx = L^-T dx~
+    if (kCoop && !kPF) f_stage_L(D, C);                         // (mv_cols ended with a block barrier; no K copy in flight)
+    f_unwhiten_x<kGL>(D, C, dxt, dxo);                          // dx = L^-T dx~
     _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) dx_out[(int64_t)qp * n + i] = qsm[dxo + i];
     _Pragma("unroll 1") for (int i = tid; i < m; i += kNT) {
         dz_out[(int64_t)qp * m + i] = qsm[w + ep + i];
@@ -1264,7 +1330,7 @@ __host__ __device__ inline SLayout setup_layout(const KDims& D) {
 __global__ void __launch_bounds__(kThreads, 1)
 k_setup_fast(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __restrict__ G, int64_t sG,
              const double* __restrict__ A, int64_t sA, double* __restrict__ Lfac, double* __restrict__ Wfac,
-             double* __restrict__ Kfac, int* __restrict__ spd_flag) {
+             double* __restrict__ Kfac, int* __restrict__ spd_flag, int pf) {
     using namespace fk;
     QPB_SMEM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1339,7 +1405,7 @@ k_setup_fast(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __
     // ---- outputs L (packed lower, true diagonal) and W (compact ms x ldw)
     double* Lg = Lfac + (int64_t)sys * D.lp;
     double* Wg = Wfac + (int64_t)sys * ms * D.ldw;
-    double* Kg = Kfac + (int64_t)sys * msp * D.lds;
+    double* Kg = Kfac + (int64_t)sys * s_doubles(D, pf != 0);
     for (int r = warp; r < n; r += kThreads / 32)
         for (int c = lane; c < r; c += 32) Lg[(r * (r + 1)) / 2 + c] = qsm[S.QA + r * ldq + c];
     for (int r = tid; r < n; r += kThreads) Lg[(r * (r + 1)) / 2 + r] = 1.0 / qsm[S.QA + r * ldq + r];   // true diagonal
@@ -1392,6 +1458,10 @@ k_setup_fast(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __
         __syncthreads();
     }
     QPB_TICK(45);   // partial chol of the equality block
+    if (pf) {                                                   // equality columns -> product form, K -> staircase
+        qpb::pf::pf_convert_cols(qsm + S.QA, D.lds, msp, ep >> 3, tid, kThreads);
+        qpb::pf::pf_write_staircase(Kg, qsm + S.QA, D.lds, msp, msp, tid, kThreads);
+    } else
     for (int i = tid; i < msp * D.lds; i += kThreads) Kg[i] = qsm[S.QA + i];
     QPB_TICK(46);   // write K
 #ifdef QPB_TIMING
@@ -1517,6 +1587,7 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
     // CTA per QP is 8 warps synchronising over a handful of rows; one warp per QP and 16 QPs per SM instead
     const bool tiny = kTinyDefault && fits && nz <= kTinyMax && msp <= kTinyMax;
     plan->tiny = tiny ? 1 : 0;
+    plan->pf = 0; plan->pf_global = 0; plan->pf_smem_bytes = 0;
     if (tiny) {
         plan->fast = 0; plan->setup_fast = 0; plan->smem_resident = 1; plan->threads = kTinyThreads;
         plan->setup_smem_bytes = (setup_mat + setup_vec) * 8;
@@ -1545,6 +1616,26 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
         plan->setup_scratch_elems = setup_mat;
         plan->solve_scratch_elems = solve_mat;
     }
+    // product-form kernels (qp_pf.cuh): factor in the staircase layout; W and chol(Q) in shared memory when they fit
+    // next to it, else read from global memory ("large problem" kernel, e.g. nz = nineq = 200). One row per thread in the
+    // substitutions: order <= 256.
+    {
+        const int64_t pf_res = (int64_t)fk::fast_smem_doubles(D, false, true) * 8;
+        const int64_t pf_glb = (int64_t)fk::fast_smem_doubles(D, true, true) * 8;
+        const bool shape_ok = msp <= kThreads && (msp - plan->neq_pad) / 8 >= 1;
+        const bool res_ok = shape_ok && pf_res <= kMaxSmem, glb_ok = shape_ok && pf_glb <= kMaxSmem;
+        int want = kPfDefault;                               // 0: only where there is no fast kernel; 1: wherever possible
+        const char* env = getenv("QPB200_PF");               // development / A-B knob: "0" never, "1" wherever possible
+        if (env != nullptr && env[0] == '0') want = -1;
+        if (env != nullptr && env[0] == '1') want = 1;
+        const bool use = (want == 1 && (res_ok || glb_ok)) || (want == 0 && !fast_ok && (res_ok || glb_ok));
+        if (use) {
+            plan->pf = 1;
+            plan->pf_global = res_ok ? 0 : 1;
+            plan->pf_smem_bytes = res_ok ? pf_res : pf_glb;
+            plan->K_elems = (int64_t)qpb::pf::pf_elems(msp >> 3);
+        }
+    }
     return QPB200_OK;
 }
 
@@ -1560,22 +1651,22 @@ int qpb200_pre_factor_kkt(const qpb200_plan* plan, int nsys, const double* Q, in
         int rc = set_smem(k_setup<true, true>, plan->setup_smem_bytes);
         if (rc) return rc;
         k_setup<true, true><<<nsys, kTinyThreads, plan->setup_smem_bytes, st>>>(D, Q, sQ, G, sG, A, sA, Lfac, Wfac, Kfac,
-                                                                                 spd_flag, nullptr, 0);
+                                                                                 spd_flag, nullptr, 0, 0);
     } else if (plan->setup_fast) {
         int rc = set_smem(k_setup_fast, plan->setup_smem_bytes);
         if (rc) return rc;
-        k_setup_fast<<<nsys, kThreads, plan->setup_smem_bytes, st>>>(D, Q, sQ, G, sG, A, sA, Lfac, Wfac, Kfac, spd_flag);
+        k_setup_fast<<<nsys, kThreads, plan->setup_smem_bytes, st>>>(D, Q, sQ, G, sG, A, sA, Lfac, Wfac, Kfac, spd_flag, plan->pf);
     } else if (plan->smem_resident) {
         int rc = set_smem(k_setup<true>, plan->setup_smem_bytes);
         if (rc) return rc;
         k_setup<true><<<nsys, kThreads, plan->setup_smem_bytes, st>>>(D, Q, sQ, G, sG, A, sA, Lfac, Wfac,
-                                                                    Kfac, spd_flag, nullptr, 0);
+                                                                    Kfac, spd_flag, nullptr, 0, plan->pf);
     } else {
         if (!scratch) return QPB200_ERR_BAD_ARG;
         int rc = set_smem(k_setup<false>, plan->setup_smem_bytes);
         if (rc) return rc;
         k_setup<false><<<nsys, kThreads, plan->setup_smem_bytes, st>>>(
-            D, Q, sQ, G, sG, A, sA, Lfac, Wfac, Kfac, spd_flag, scratch, plan->setup_scratch_elems);
+            D, Q, sQ, G, sG, A, sA, Lfac, Wfac, Kfac, spd_flag, scratch, plan->setup_scratch_elems, plan->pf);
     }
     CK(cudaGetLastError());
     return QPB200_OK;
@@ -1607,6 +1698,17 @@ int qpb200_forward(const qpb200_plan* plan, int nbatch, const double* p, int64_t
         k_forward<true, false, true><<<nbatch, kTinyThreads, plan->solve_smem_bytes, st>>>(
             D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, maxIter, zhat, lam,
             slacks, nus, iters, best_resid, trace, nullptr, 0);
+    } else if (plan->pf) {
+#define QPB_LAUNCH_PF(KG)                                                                               \
+        do {                                                                                            \
+            int rc = set_smem(k_forward_fast<KG, true>, plan->pf_smem_bytes);                           \
+            if (rc) return rc;                                                                          \
+            k_forward_fast<KG, true><<<nbatch, kThreads, plan->pf_smem_bytes, st>>>(                    \
+                D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, \
+                maxIter, zhat, lam, slacks, nus, iters, best_resid, trace);                             \
+        } while (0)
+        if (plan->pf_global) QPB_LAUNCH_PF(true); else QPB_LAUNCH_PF(false);
+#undef QPB_LAUNCH_PF
     } else if (plan->fast && plan->coop && plan->coop_ok) {
         int rc = set_smem(k_forward_fast<true>, plan->coop_smem_bytes);
         if (rc) return rc;
@@ -1654,6 +1756,16 @@ int qpb200_solve_kkt(const qpb200_plan* plan, int nbatch, const double* d, const
         if (rc) return rc;
         k_solve_kkt<true, false, false, true><<<nbatch, kTinyThreads, plan->solve_smem_bytes, st>>>(
             D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz, dy, O, nullptr, 0);
+    } else if (plan->pf) {
+#define QPB_LAUNCH_PF(KG)                                                                               \
+        do {                                                                                            \
+            int rc = set_smem(k_kkt_fast<false, KG, true>, plan->pf_smem_bytes);                        \
+            if (rc) return rc;                                                                          \
+            k_kkt_fast<false, KG, true><<<nbatch, kThreads, plan->pf_smem_bytes, st>>>(                 \
+                D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz, dy, O); \
+        } while (0)
+        if (plan->pf_global) QPB_LAUNCH_PF(true); else QPB_LAUNCH_PF(false);
+#undef QPB_LAUNCH_PF
     } else if (plan->fast && plan->coop && plan->coop_ok) {
         int rc = set_smem(k_kkt_fast<false, true>, plan->coop_smem_bytes);
         if (rc) return rc;
@@ -1705,6 +1817,17 @@ int qpb200_backward(const qpb200_plan* plan, int nbatch, const double* dl_dzhat,
         k_solve_kkt<true, false, true, true><<<nbatch, kTinyThreads, plan->solve_smem_bytes, st>>>(
             D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac, sF, dxv, nullptr,
             dlamv, dnuv, O, nullptr, 0);
+    } else if (plan->pf) {
+#define QPB_LAUNCH_PF(KG)                                                                               \
+        do {                                                                                            \
+            int rc = set_smem(k_kkt_fast<true, KG, true>, plan->pf_smem_bytes);                         \
+            if (rc) return rc;                                                                          \
+            k_kkt_fast<true, KG, true><<<nbatch, kThreads, plan->pf_smem_bytes, st>>>(                  \
+                D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac, sF, dxv, \
+                nullptr, dlamv, dnuv, O);                                                               \
+        } while (0)
+        if (plan->pf_global) QPB_LAUNCH_PF(true); else QPB_LAUNCH_PF(false);
+#undef QPB_LAUNCH_PF
     } else if (plan->fast && plan->coop && plan->coop_ok) {
         int rc = set_smem(k_kkt_fast<true, true>, plan->coop_smem_bytes);
         if (rc) return rc;

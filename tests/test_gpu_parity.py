@@ -57,6 +57,12 @@ EXPECTED_PATH = {
 }
 
 
+# product-form kernels (qp_pf.cuh) by default only where no fast kernel exists: (pf, pf_global)
+EXPECTED_PF = {"band_smem": (1, 0), "band_smem_eq": (1, 0), "c4": (1, 1)}
+# cases re-run with QPB200_PF=1 (product-form kernels wherever they fit): every non-tiny kernel family
+PF_CASES = ["c2", "c3_b64", "c4_small", "c5_shard0", "band_setup", "band_setup_eq", "band_smem_eq", "c4"]
+
+
 def _report(name, errs):
     """Append worst errors of a case to gpurun_out/parity_report.jsonl (copied to profiles/ by hand)."""
     import json, os
@@ -82,10 +88,42 @@ def test_matches_reference_golden(name, golden_dir):
                              np.asarray(prob["A"]).shape[-2] if np.asarray(prob["A"]).size else 0)
         assert (plan.fast, plan.setup_fast, plan.smem_resident) == EXPECTED_PATH[name], name
         assert plan.tiny == 0
+        assert (plan.pf, plan.pf_global) == EXPECTED_PF.get(name, (0, 0)), name
     if name in EXPECTED_TINY:       # one warp per QP (nz, ms_pad <= 32): the sizes of the reference's own tests
         Qs, Gs, As = np.asarray(prob["Q"]), np.asarray(prob["G"]), np.asarray(prob["A"])
         plan = _lib.plan_for(Qs.shape[-1], Gs.shape[-2], As.shape[-2] if As.size else 0)
         assert plan.tiny == 1 and plan.threads == 32, name
+
+
+@pytest.mark.parametrize("name", PF_CASES)
+def test_product_form_kernels_match_golden(name, golden_dir, monkeypatch):
+    """The product-form / staircase kernels (plan.pf) forced on every shape they support, against the real reference."""
+    from qpth_b200 import _lib
+    monkeypatch.setenv("QPB200_PF", "1")
+    prob, gold, full = load_case(name, golden_dir)
+    Qs, Gs, As = np.asarray(prob["Q"]), np.asarray(prob["G"]), np.asarray(prob["A"])
+    plan = _lib.plan_for(Qs.shape[-1], Gs.shape[-2], As.shape[-2] if As.size else 0)
+    assert plan.pf == 1, name
+    out = _run(prob)
+    errs = check_against_golden(out, gold, full, what=name + "[pf]", prob=prob)
+    _report(name + "[pf]", errs)
+
+
+@pytest.mark.parametrize("name", SWEEP)
+def test_randomised_sweep_product_form(name, golden_dir, monkeypatch):
+    """The randomised sweep (ill-conditioned Q, wide range of d) through the product-form kernels."""
+    from qpth_b200 import _lib
+    from tests.parity import check_sweep
+    monkeypatch.setenv("QPB200_PF", "1")
+    prob, gold, full = load_case(name, golden_dir)
+    Qs, Gs, As = np.asarray(prob["Q"]), np.asarray(prob["G"]), np.asarray(prob["A"])
+    plan = _lib.plan_for(Qs.shape[-1], Gs.shape[-2], As.shape[-2] if As.size else 0)
+    if plan.tiny:
+        pytest.skip("one-warp-per-QP shape: no product-form kernel")
+    assert plan.pf == 1, name
+    out = _run(prob)
+    r = check_sweep(out, prob, gold, what=name + "[pf]")
+    _report(name + "[pf]", {k: v for k, v in r.items() if k in ("z", "dQ", "dp", "dG", "dh", "dA", "db", "ref_kkt", "our_kkt")})
 
 
 @pytest.mark.parametrize("name", SWEEP)
