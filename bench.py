@@ -233,6 +233,13 @@ def e2e_leg(f, dev, rank, world, nsteps_req, warmup, dl):
 def run_b200(args, rank, world, local_rank):
     numa = bind_to_gpu_numa(local_rank)
     from qpth_b200 import QPFunction, _lib
+    from qpth_b200 import qp as qpmod
+    # Every leg of this bench keeps several steps (batches) in flight on several CUDA streams, i.e. more QPs than the
+    # GPU has SMs: the library's throughput mode (two QPs per SM; qpth_b200.qp.MODE, a documented user switch whose
+    # "auto" default picks it for any batch larger than the SM count). The single-stream figure (detail.serial_*) is
+    # taken in latency mode (one QP per SM), the right choice for ONE 128-QP batch at a time.
+    bench_mode = os.environ.get("QPB_BENCH_MODE", "throughput")
+    qpmod.MODE = bench_mode
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     lib = _lib.load()
@@ -256,36 +263,50 @@ def run_b200(args, rank, world, local_rank):
     # forward/backward call) so that the timed loop is not at the mercy of host jitter. Falls back to eager.
     launch_mode = "eager"
     last_iters = None
-    if os.environ.get("QPB_BENCH_GRAPHS", "1") == "1":
+    serial_step = None
+
+    def capture_graphs():
         from qpth_b200.qp import solve_forward, solve_backward
+        flags, want = [False] * 6, [True, True, True, True, False, False]
+
+        def raw_step(t):
+            st_ = solve_forward(t["Q"].detach(), t["p"].detach(), t["G"].detach(), t["h"].detach(), e, e,
+                                verbose=-1, check_Q_spd=False)
+            return st_, solve_backward(st_, dl, flags, want)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for t in batches[:2]:
+                raw_step(t)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graphs, keep = [], []
+        for t in batches:
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                keep.append(raw_step(t))
+            graphs.append(gph)
+        return graphs, keep
+
+    if os.environ.get("QPB_BENCH_GRAPHS", "1") == "1":
         try:
-            flags, want = [False] * 6, [True, True, True, True, False, False]
-
-            def raw_step(t):
-                st_ = solve_forward(t["Q"].detach(), t["p"].detach(), t["G"].detach(), t["h"].detach(), e, e,
-                                    verbose=-1, check_Q_spd=False)
-                return st_, solve_backward(st_, dl, flags, want)
-
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for t in batches[:2]:
-                    raw_step(t)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graphs, keep = [], []
-            for t in batches:
-                gph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gph):
-                    keep.append(raw_step(t))
-                graphs.append(gph)
+            graphs, keep = capture_graphs()
 
             def step(i):                                          # noqa: F811
                 graphs[i % NCOPIES].replay()
             last_iters = keep[-1][0].iters
             launch_mode = "cuda_graph"
+            if bench_mode != "latency":                           # the single-stream leg: one QP per SM
+                qpmod.MODE = "latency"
+                lat_graphs, lat_keep = capture_graphs()
+                qpmod.MODE = bench_mode
+
+                def serial_step(i):                               # noqa: F811
+                    lat_graphs[i % NCOPIES].replay()
         except Exception as exc:                                  # noqa: BLE001
             sys.stderr.write("bench: CUDA graph capture failed (%s); using the eager loop\n" % str(exc)[:200])
+            qpmod.MODE = bench_mode
             torch.cuda.synchronize()
     # `value`: K steps with the inputs resident in HBM. A step's kernels have 128 CTAs (one QP each); the GPU holds
     # 148 (one QP per SM) or 296 (co-resident kernels) at a time and a QP leaves its slot as soon as it has converged
@@ -302,8 +323,9 @@ def run_b200(args, rank, world, local_rank):
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record()
         if streams is None:
+            one = serial_step if serial_step is not None else step
             for i in range(nsteps):
-                step(first + i)
+                one(first + i)
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             torch.cuda.synchronize()
@@ -325,6 +347,7 @@ def run_b200(args, rank, world, local_rank):
     done = settle_steps
     timed_window(args.steps, done, use_streams)       # untimed rehearsal: same run-ahead, same allocation pattern
     done += args.steps
+    timed_window(max(4, args.steps // 2), done, None)
     serial_ms = timed_window(args.steps, done, None)  # informational: one stream, steps strictly back to back
     done += args.steps
     torch.cuda.synchronize()
@@ -364,7 +387,7 @@ def run_b200(args, rank, world, local_rank):
         return None
 
     # ---- the three kernels timed alone through the C ABI, on the stream they are launched on
-    plan = _lib.plan_for(n, m, 0)
+    plan = _lib.plan_for(n, m, 0, two=(bench_mode == "throughput"))      # the kernels the timed region ran
     t = batches[0]
     f64 = dict(dtype=torch.float64, device=dev)
     L = torch.empty(B * plan.L_elems, **f64); W = torch.empty(B * plan.W_elems, **f64)
@@ -455,7 +478,9 @@ def run_b200(args, rank, world, local_rank):
         "detail": {"l2": "inputs rotate over %d independent batches (%.0f MB > 126 MB L2)" % (NCOPIES, NCOPIES * h2d / 1e6),
                    "mean_newton_iters": iters_mean, "launch": launch_mode, "steps_in_flight": inflight,
                    "serial_ms_per_step": serial_ms / args.steps, "serial_value": total_qps / (serial_ms * 1e-3),
-                   "settle_steps": settle_steps, "numa": numa, "solve_kernels": "co-resident (2 QPs/SM)" if plan.coop else "one QP per SM",
+                   "settle_steps": settle_steps, "numa": numa, "mode": bench_mode,
+                   "solve_kernels": ("product form" if plan.pf else "round-1") + (", two QPs per SM (W, chol(Q) from L2)" if (plan.pf and plan.pf_two) else ", one QP per SM"),
+                   "serial_kernels": "one QP per SM (latency mode)" if serial_step is not None else "same as value",
                    "kernel_ms_alone": {"setup": setup_ms, "forward": k_ms, "backward": bwd_ms}},
     }
     if world == 1 and os.environ.get("QPB_BENCH_C4", "1") == "1":

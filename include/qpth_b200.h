@@ -69,6 +69,12 @@ typedef struct qpb200_plan {
     int pf_global;          /* with pf: 1 = W and chol(Q) are read from global memory (large problems, e.g. nz = nineq =
                              *    200: factor + vectors fill the shared memory), 0 = staged in shared memory             */
     int64_t pf_smem_bytes;  /* dynamic shared memory of the product-form solve kernels */
+    int pf2_ok;             /* with pf: 1 = the two-QPs-per-SM variant of the solve kernels exists for this shape (factor and
+                             *    vectors of a QP take <= 113 KB; W and chol(Q) are read from L2; 128 registers per thread)  */
+    int pf_two;             /* with pf2_ok: 1 = use it. THE CALLER MAY SET THIS per call: two QPs per SM give the higher
+                             *    throughput once more QPs are in flight than the GPU has SMs (a large batch, or several
+                             *    batches on several streams); one QP per SM has the lower latency for a small batch.      */
+    int64_t pf2_smem_bytes; /* dynamic shared memory of the two-QPs-per-SM variant */
 } qpb200_plan;
 
 int qpb200_version(void);

@@ -26,6 +26,7 @@ class Plan(ctypes.Structure):
         ("setup_smem_bytes", ctypes.c_int64), ("solve_smem_bytes", ctypes.c_int64),
         ("coop_smem_bytes", ctypes.c_int64), ("coop_ok", ctypes.c_int), ("coop", ctypes.c_int), ("tiny", ctypes.c_int),
         ("pf", ctypes.c_int), ("pf_global", ctypes.c_int), ("pf_smem_bytes", ctypes.c_int64),
+        ("pf2_ok", ctypes.c_int), ("pf_two", ctypes.c_int), ("pf2_smem_bytes", ctypes.c_int64),
     ]
 
 
@@ -85,14 +86,30 @@ def check(rc):
 _plans = {}
 
 
-def plan_for(nz, nineq, neq):
-    # QPB200_PF (development / A-B knob read by qpb200_plan_init: "0" never, "1" product-form kernels wherever they fit)
-    key = (nz, nineq, neq, os.environ.get("QPB200_PF"))
+def plan_for(nz, nineq, neq, two=None):
+    """Plan for a shape (cached). `two`: None = the library default; True / False = select / deselect the
+    two-QPs-per-SM variant of the product-form solve kernels when the shape has one (plan.pf2_ok). Every
+    (shape, two) pair has its own Plan object, so concurrent callers never see each other's choice."""
+    # QPB200_PF (development / A-B knob read by qpb200_plan_init: "0" never, "1" product-form kernels wherever they fit,
+    # "2" = "1" + the two-QPs-per-SM variant by default)
+    key = (nz, nineq, neq, os.environ.get("QPB200_PF"), None if two is None else bool(two))
     if key not in _plans:
         p = Plan()
         rc = load().qpb200_plan_init(nz, nineq, neq, ctypes.byref(p))
         check(rc)
         if os.environ.get("QPB200_COOP") is not None and p.coop_ok:     # development knob: force a kernel family
             p.coop = 1 if os.environ["QPB200_COOP"] == "1" else 0
+        if two is not None and p.pf2_ok:
+            p.pf_two = 1 if two else 0
         _plans[key] = p
     return _plans[key]
+
+
+_sm_count = {}
+
+
+def sm_count(device_index):
+    if device_index not in _sm_count:
+        import torch
+        _sm_count[device_index] = torch.cuda.get_device_properties(device_index).multi_processor_count
+    return _sm_count[device_index]

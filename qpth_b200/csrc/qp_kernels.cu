@@ -44,9 +44,14 @@ constexpr int kCoopDefault = QPB_COOP_DEFAULT;
 #endif
 constexpr int kTinyDefault = QPB_TINY_DEFAULT;
 #ifndef QPB_PF_DEFAULT
-#define QPB_PF_DEFAULT 0       // product-form kernels: 0 = only for shapes without a fast kernel, 1 = wherever they fit
+#define QPB_PF_DEFAULT 1       // product-form kernels: 0 = only for shapes without a fast kernel, 1 = wherever they fit
+                               // (measured r2c-r2g: never slower than the round-1 kernels: C2 -1.6 %, C3 -10 %, C4 2.6x faster)
 #endif
 constexpr int kPfDefault = QPB_PF_DEFAULT;
+#ifndef QPB_PF_TWO_DEFAULT
+#define QPB_PF_TWO_DEFAULT 0   // 1: prefer the two-QPs-per-SM product-form kernels (W, L from L2) where they fit
+#endif
+constexpr int kPfTwoDefault = QPB_PF_TWO_DEFAULT;
 constexpr int kMaxSmem = 232448 - 1024;   // 227 KB opt-in limit per CTA on sm_100, minus static smem slack
 
 struct KDims {
@@ -746,7 +751,7 @@ __host__ __device__ inline FLayout fast_layout(const KDims& D, bool coop, bool p
     L.W = 0;
     L.LS = coop ? 0 : L.W + D.ms * D.ldw;
     L.pan = L.LS + s_doubles(D, pf);
-    const int after_s = L.pan + (pf ? D.msp * qpb::pf::kPanLd : 0);
+    const int after_s = L.pan + (pf ? (D.msp + 8) * qpb::pf::kPanLd : 0);
     L.Lp = coop ? L.LS : after_s;
     L.vec = coop ? after_s : L.Lp + D.lp;
     L.red = L.vec + F_COUNT * L.vl;
@@ -942,8 +947,10 @@ __device__ __forceinline__ double f_step_fix(double v) { return (isinf(v) && v >
 // kCoop: co-resident mode (two CTAs per SM; W and L read from global memory, see qp_fast.cuh).
 // kPF: product-form factor in the staircase layout (qp_pf.cuh); with kCoop it is the "large problem" kernel: factor
 // and vectors in shared memory, W and L read from global memory (L2-resident when the system is shared), ONE CTA per SM.
-template <bool kCoop, bool kPF = false>
-__global__ void __launch_bounds__(kThreads, (kCoop && !kPF) ? 2 : 1)
+// kTwo (with kCoop && kPF): the same kernel compiled for TWO CTAs per SM (128 registers): 78 KB of shared memory per QP at
+// C2, so two QPs share an SM and fill each other's pivot-chain bubbles.
+template <bool kCoop, bool kPF = false, bool kTwo = false>
+__global__ void __launch_bounds__(kThreads, ((kCoop && !kPF) || kTwo) ? 2 : 1)
 k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* __restrict__ h, int64_t sh,
                const double* __restrict__ b, int64_t sb, const double* __restrict__ Lfac,
                const double* __restrict__ Wfac, const double* __restrict__ Kfac, int sF, double eps,
@@ -1113,6 +1120,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         if (kPF) {
             qpb::pf::pf_solve(C.L.LS, msp, t1, t0, hW);         // (hW is dead until the combined direction below)
             wc = hW;
+            QPB_TICK(12);
         } else {
 #if QPB_PFORM
         f_ptrsv_fwd(C.L.LS, D.lds, msp, t1, t0);
@@ -1188,8 +1196,8 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
 #endif
 }
 
-template <bool kBackward, bool kCoop, bool kPF = false>
-__global__ void __launch_bounds__(kThreads, (kCoop && !kPF) ? 2 : 1)
+template <bool kBackward, bool kCoop, bool kPF = false, bool kTwo = false>
+__global__ void __launch_bounds__(kThreads, ((kCoop && !kPF) || kTwo) ? 2 : 1)
 k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ rx_in,
            const double* __restrict__ rs_in, const double* __restrict__ rz_in,
            const double* __restrict__ ry_in, const double* __restrict__ zhat,
@@ -1587,7 +1595,7 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
     // CTA per QP is 8 warps synchronising over a handful of rows; one warp per QP and 16 QPs per SM instead
     const bool tiny = kTinyDefault && fits && nz <= kTinyMax && msp <= kTinyMax;
     plan->tiny = tiny ? 1 : 0;
-    plan->pf = 0; plan->pf_global = 0; plan->pf_smem_bytes = 0;
+    plan->pf = 0; plan->pf_global = 0; plan->pf_smem_bytes = 0; plan->pf2_ok = 0; plan->pf2_smem_bytes = 0; plan->pf_two = 0;
     if (tiny) {
         plan->fast = 0; plan->setup_fast = 0; plan->smem_resident = 1; plan->threads = kTinyThreads;
         plan->setup_smem_bytes = (setup_mat + setup_vec) * 8;
@@ -1625,14 +1633,19 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
         const bool shape_ok = msp <= kThreads && (msp - plan->neq_pad) / 8 >= 1;
         const bool res_ok = shape_ok && pf_res <= kMaxSmem, glb_ok = shape_ok && pf_glb <= kMaxSmem;
         int want = kPfDefault;                               // 0: only where there is no fast kernel; 1: wherever possible
-        const char* env = getenv("QPB200_PF");               // development / A-B knob: "0" never, "1" wherever possible
-        if (env != nullptr && env[0] == '0') want = -1;
-        if (env != nullptr && env[0] == '1') want = 1;
+        const char* env = getenv("QPB200_PF");               // development / A-B knob: "0" never, "1" wherever possible,
+        if (env != nullptr && env[0] == '0') want = -1;      // "2" = "1" + two QPs per SM (W, L from L2) where that fits
+        if (env != nullptr && (env[0] == '1' || env[0] == '2')) want = 1;
+        const bool two_ok = glb_ok && pf_glb <= (232448 / 2 - 1024 - 64);
+        const bool want_two = (env != nullptr && env[0] == '2') || (env == nullptr && kPfTwoDefault);
         const bool use = (want == 1 && (res_ok || glb_ok)) || (want == 0 && !fast_ok && (res_ok || glb_ok));
         if (use) {
             plan->pf = 1;
             plan->pf_global = res_ok ? 0 : 1;
             plan->pf_smem_bytes = res_ok ? pf_res : pf_glb;
+            plan->pf2_ok = two_ok ? 1 : 0;
+            plan->pf2_smem_bytes = two_ok ? pf_glb : 0;
+            plan->pf_two = (two_ok && want_two) ? 1 : 0;
             plan->K_elems = (int64_t)qpb::pf::pf_elems(msp >> 3);
         }
     }
@@ -1699,15 +1712,18 @@ int qpb200_forward(const qpb200_plan* plan, int nbatch, const double* p, int64_t
             D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, maxIter, zhat, lam,
             slacks, nus, iters, best_resid, trace, nullptr, 0);
     } else if (plan->pf) {
-#define QPB_LAUNCH_PF(KG)                                                                               \
+#define QPB_LAUNCH_PF(KG, K2)                                                                           \
         do {                                                                                            \
-            int rc = set_smem(k_forward_fast<KG, true>, plan->pf_smem_bytes);                           \
+            const size_t sb_ = K2 ? plan->pf2_smem_bytes : plan->pf_smem_bytes;                         \
+            int rc = set_smem(k_forward_fast<KG, true, K2>, sb_);                                       \
             if (rc) return rc;                                                                          \
-            k_forward_fast<KG, true><<<nbatch, kThreads, plan->pf_smem_bytes, st>>>(                    \
+            k_forward_fast<KG, true, K2><<<nbatch, kThreads, sb_, st>>>(                                \
                 D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, \
                 maxIter, zhat, lam, slacks, nus, iters, best_resid, trace);                             \
         } while (0)
-        if (plan->pf_global) QPB_LAUNCH_PF(true); else QPB_LAUNCH_PF(false);
+        if (plan->pf_two && plan->pf2_ok) QPB_LAUNCH_PF(true, true);
+        else if (plan->pf_global) QPB_LAUNCH_PF(true, false);
+        else QPB_LAUNCH_PF(false, false);
 #undef QPB_LAUNCH_PF
     } else if (plan->fast && plan->coop && plan->coop_ok) {
         int rc = set_smem(k_forward_fast<true>, plan->coop_smem_bytes);
@@ -1757,14 +1773,17 @@ int qpb200_solve_kkt(const qpb200_plan* plan, int nbatch, const double* d, const
         k_solve_kkt<true, false, false, true><<<nbatch, kTinyThreads, plan->solve_smem_bytes, st>>>(
             D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz, dy, O, nullptr, 0);
     } else if (plan->pf) {
-#define QPB_LAUNCH_PF(KG)                                                                               \
+#define QPB_LAUNCH_PF(KG, K2)                                                                           \
         do {                                                                                            \
-            int rc = set_smem(k_kkt_fast<false, KG, true>, plan->pf_smem_bytes);                        \
+            const size_t sb_ = K2 ? plan->pf2_smem_bytes : plan->pf_smem_bytes;                         \
+            int rc = set_smem(k_kkt_fast<false, KG, true, K2>, sb_);                                    \
             if (rc) return rc;                                                                          \
-            k_kkt_fast<false, KG, true><<<nbatch, kThreads, plan->pf_smem_bytes, st>>>(                 \
+            k_kkt_fast<false, KG, true, K2><<<nbatch, kThreads, sb_, st>>>(                             \
                 D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz, dy, O); \
         } while (0)
-        if (plan->pf_global) QPB_LAUNCH_PF(true); else QPB_LAUNCH_PF(false);
+        if (plan->pf_two && plan->pf2_ok) QPB_LAUNCH_PF(true, true);
+        else if (plan->pf_global) QPB_LAUNCH_PF(true, false);
+        else QPB_LAUNCH_PF(false, false);
 #undef QPB_LAUNCH_PF
     } else if (plan->fast && plan->coop && plan->coop_ok) {
         int rc = set_smem(k_kkt_fast<false, true>, plan->coop_smem_bytes);
@@ -1818,15 +1837,18 @@ int qpb200_backward(const qpb200_plan* plan, int nbatch, const double* dl_dzhat,
             D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac, sF, dxv, nullptr,
             dlamv, dnuv, O, nullptr, 0);
     } else if (plan->pf) {
-#define QPB_LAUNCH_PF(KG)                                                                               \
+#define QPB_LAUNCH_PF(KG, K2)                                                                           \
         do {                                                                                            \
-            int rc = set_smem(k_kkt_fast<true, KG, true>, plan->pf_smem_bytes);                         \
+            const size_t sb_ = K2 ? plan->pf2_smem_bytes : plan->pf_smem_bytes;                         \
+            int rc = set_smem(k_kkt_fast<true, KG, true, K2>, sb_);                                     \
             if (rc) return rc;                                                                          \
-            k_kkt_fast<true, KG, true><<<nbatch, kThreads, plan->pf_smem_bytes, st>>>(                  \
+            k_kkt_fast<true, KG, true, K2><<<nbatch, kThreads, sb_, st>>>(                              \
                 D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac, sF, dxv, \
                 nullptr, dlamv, dnuv, O);                                                               \
         } while (0)
-        if (plan->pf_global) QPB_LAUNCH_PF(true); else QPB_LAUNCH_PF(false);
+        if (plan->pf_two && plan->pf2_ok) QPB_LAUNCH_PF(true, true);
+        else if (plan->pf_global) QPB_LAUNCH_PF(true, false);
+        else QPB_LAUNCH_PF(false, false);
 #undef QPB_LAUNCH_PF
     } else if (plan->fast && plan->coop && plan->coop_ok) {
         int rc = set_smem(k_kkt_fast<true, true>, plan->coop_smem_bytes);

@@ -33,9 +33,9 @@ __host__ __device__ __forceinline__ int pf_rowoff(int r) {
 __host__ __device__ __forceinline__ int pf_elems(int nts) { return (32 * nts + 64) * nts; }
 constexpr int kPanLd = 12;              // row stride of the panel scratch (8 used)
 
-// In-register factorization of an 8x8 SPD block (lower triangle in Lk) and the inverse of its factor.
-// On exit Tk = L^-1 (lower triangle incl. diagonal); Lk is scratch. A non-positive pivot gives NaN/inf everywhere below it.
-__device__ __forceinline__ void pf_factor8_inv(double (&Lk)[36], double (&Tk)[36]) {
+// In-register factorization of an 8x8 SPD block (lower triangle in Lk, every lane holds all of it): on exit strictly
+// lower = L, diagonal = 1 / L_cc. A non-positive pivot gives NaN/inf everywhere below it.
+__device__ __forceinline__ void pf_factor8(double (&Lk)[36]) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const double ri = f_rsqrt(Lk[QPB_LIDX(c, c)]);
@@ -48,17 +48,18 @@ __device__ __forceinline__ void pf_factor8_inv(double (&Lk)[36], double (&Tk)[36
             for (int cc = c + 1; cc <= r; ++cc)
                 Lk[QPB_LIDX(r, cc)] = fma(-Lk[QPB_LIDX(r, c)], Lk[QPB_LIDX(cc, c)], Lk[QPB_LIDX(r, cc)]);
     }
-    // T = L^-1, column by column: T[c][c] = 1/L_cc, T[r][c] = -(sum_{j=c}^{r-1} L[r][j] T[j][c]) / L_rr
+}
+// Column c = lane & 7 of T = L^-1 from the factored block (every lane holds Lk; the lane dependence is in predicates
+// only, so the eight columns are computed side by side instead of one lane doing all 112 operations):
+//   T[c][c] = 1/L_cc,  T[r][c] = -(sum_{j=c}^{r-1} L[r][j] T[j][c]) / L_rr  (r > c),  0 above the diagonal.
+__device__ __forceinline__ void pf_inv8_col(const double (&Lk)[36], int c, double (&Tc)[8]) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        Tk[QPB_LIDX(c, c)] = Lk[QPB_LIDX(c, c)];
+    for (int r = 0; r < 8; ++r) {
+        double sacc = 0.0;
 #pragma unroll
-        for (int r = c + 1; r < 8; ++r) {
-            double sacc = Lk[QPB_LIDX(r, c)] * Tk[QPB_LIDX(c, c)];
-#pragma unroll
-            for (int j = c + 1; j < r; ++j) sacc = fma(Lk[QPB_LIDX(r, j)], Tk[QPB_LIDX(j, c)], sacc);
-            Tk[QPB_LIDX(r, c)] = -Lk[QPB_LIDX(r, r)] * sacc;
-        }
+        for (int j = 0; j < r; ++j) sacc = fma((j >= c) ? Lk[QPB_LIDX(r, j)] : 0.0, (j >= c) ? Tc[j] : 0.0, sacc);
+        const double dr = Lk[QPB_LIDX(r, r)];
+        Tc[r] = (r < c) ? 0.0 : ((r == c) ? dr : -dr * sacc);
     }
 }
 
@@ -91,20 +92,21 @@ __device__ __forceinline__ void pf_store_lower8(double* M, int r0, int c0, const
 // block of pre_factor_kkt, batch.py:402-424) with their contribution already subtracted from the trailing block.
 // aug (offset): right-hand side carried along as a RUNNING right-hand side b (the caller has already swept the block
 // columns < kb0 over it with pf_fwd): on exit aug = b with  y_k = T_k b_k  still to be applied (pf_diag).
-// pan (offset): panel scratch, 8 nts rows x kPanLd.
+// pan (offset): panel scratch, (8 nts + 8) rows x kPanLd.
 // Roles: warp 0 = the pivot chain (F_k, the tile below it, the next diagonal tile, F_k+1), warps 1.. = panel + trailing
-// update. Named barrier 1: T_k published (chain arrives, update warps wait); named barrier 2: panel complete (update
-// warps only); one __syncthreads per step. blockDim.x == kNT.
+// update. Named barrier 1: T_k published (chain arrives, update warps wait); named barrier 2: panel complete (chain
+// arrives, update warps wait); one __syncthreads per step. blockDim.x == kNT.
 __device__ __noinline__ void pf_chol_chain(int S, int nts, int kb0, int pan) {
     QPB_SMEM;
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     double* M = qsm + S;
     double* P = qsm + pan;
-    double Lk[36], Tk[36];
+    double Lk[36], Tc[8];                                   // Tc: column (lane & 7) of T_k
     pf_load_lower8(M, 8 * kb0, 8 * kb0, Lk);
     __syncwarp();
-    pf_factor8_inv(Lk, Tk);
+    pf_factor8(Lk);
+    pf_inv8_col(Lk, lane & 7, Tc);
 #pragma unroll 1
     for (int k = kb0; k < nts; ++k) {
         const int k0 = 8 * k;
@@ -112,9 +114,16 @@ __device__ __noinline__ void pf_chol_chain(int S, int nts, int kb0, int pan) {
         const int rn = pf_rowoff(k0 + 8 + g);               // this lane's row of block k+1 (only used if `more`)
         double a0 = 0.0, a1 = 0.0;
         if (more) { a0 = M[rn + k0 + q]; a1 = M[rn + k0 + q + 4]; }   // A_{k+1,k} BEFORE its owner overwrites it with P
-        if (lane == 0) pf_store_lower8(M, k0, k0, Tk);      // publish T_k in the diagonal tile
+        if (lane < 8) {                                      // publish T_k in the diagonal tile: lane c stores column c
+            const int ldk = 8 * k + 12;
+            double* Tb = M + (32 * k + 64) * k + k0 + lane;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r >= lane) Tb[r * ldk] = Tc[r];
+        }
         __syncwarp();
         named_bar_arrive(1, kNT);
+        if (k < 16) QPB_TICK(96 + k);   // publish T_k
         if (more) {
             // L_{k+1,k} = A T_k^T : B[kk][nn] = T[nn][kk]
             const int rk = pf_rowoff(k0 + g) + k0;
@@ -124,6 +133,7 @@ __device__ __noinline__ void pf_chol_chain(int S, int nts, int kb0, int pan) {
             dmma884(d0, d1, a1, bT1);
             *reinterpret_cast<double2*>(P + (k0 + 8 + g) * kPanLd + 2 * q) = make_double2(d0, d1);
             __syncwarp();
+            named_bar_arrive(2, kNT);                        // the panel rows of block k+1 are in the scratch
             const double la0 = P[(k0 + 8 + g) * kPanLd + q], la1 = P[(k0 + 8 + g) * kPanLd + q + 4];
             // diagonal tile k+1 -= L L^T
             double2 cv = *reinterpret_cast<const double2*>(M + rn + k0 + 8 + 2 * q);
@@ -131,11 +141,17 @@ __device__ __noinline__ void pf_chol_chain(int S, int nts, int kb0, int pan) {
             dmma884(cv.x, cv.y, -la1, la1);
             *reinterpret_cast<double2*>(M + rn + k0 + 8 + 2 * q) = cv;
             __syncwarp();
+            QPB_TICK(24);               // tile below + next diagonal tile
             pf_load_lower8(M, k0 + 8, k0 + 8, Lk);
             __syncwarp();
-            pf_factor8_inv(Lk, Tk);                          // F_{k+1}, T_{k+1}
+            pf_factor8(Lk);                                  // F_{k+1}
+            pf_inv8_col(Lk, lane & 7, Tc);                   // T_{k+1}
+            if (k < 16) QPB_TICK(80 + k);   // F_{k+1}
+        } else {
+            named_bar_arrive(2, kNT);
         }
         __syncthreads();
+        if (k < 16) QPB_TICK(112 + k);      // chain warp waiting for the update warps
     }
 }
 
@@ -149,7 +165,9 @@ __device__ __noinline__ void pf_chol_update(int S, int nts, int kb0, int aug, in
 #pragma unroll 1
     for (int k = kb0; k < nts; ++k) {
         const int k0 = 8 * k;
+        QPB_TICK1(40);
         named_bar_sync(1, kNT);                              // T_k is in the diagonal tile
+        QPB_TICK1(42);
         {
             const int rg = pf_rowoff(k0 + g) + k0, rq = pf_rowoff(k0 + q) + k0 + g;
             const int ld4 = 4 * (8 * k + 12);
@@ -164,16 +182,20 @@ __device__ __noinline__ void pf_chol_update(int S, int nts, int kb0, int aug, in
                 double d0 = 0.0, d1 = 0.0;
                 dmma884(d0, d1, a0, bT0);
                 dmma884(d0, d1, a1, bT1);
-                *reinterpret_cast<double2*>(P + r * kPanLd + 2 * q) = make_double2(d0, d1);
+                // rows of block k+1 belong to the chain warp in the shared scratch: keep a private copy past its end
+                double* pl = P + ((i == k + 1) ? (8 * nts + g) : r) * kPanLd;
+                *reinterpret_cast<double2*>(pl + 2 * q) = make_double2(d0, d1);
                 __syncwarp();
-                const double la0 = P[r * kPanLd + q], la1 = P[r * kPanLd + q + 4];
+                const double la0 = pl[q], la1 = pl[q + 4];
                 double e0 = 0.0, e1 = 0.0;
                 dmma884(e0, e1, la0, bP0);
                 dmma884(e0, e1, la1, bP1);
                 *reinterpret_cast<double2*>(row + 2 * q) = make_double2(e0, e1);
             }
         }
-        named_bar_sync(2, kNT - 32);                          // every panel row of this step is in the scratch, every P_ik in place
+        if (k < 16) QPB_TICK1(64 + k);      // S_k
+        named_bar_sync(2, kNT);                               // every panel row of this step is in the scratch (the chain warp's too), every P_ik in place
+        QPB_TICK1(43);                      // waiting for the panel
         // running right-hand side: b_r -= P[r][k0 .. k0+7] . b_k, one row per thread (no shuffles: under this warp-role
         // branch they take their divergent fallback, profiles/r1_experiments.md finding 3)
 #pragma unroll 1
@@ -186,41 +208,51 @@ __device__ __noinline__ void pf_chol_update(int S, int nts, int kb0, int aug, in
             for (int c = 0; c < 8; c += 2) { s0 = fma(-pr[c], y[c], s0); s1 = fma(-pr[c + 1], y[c + 1], s1); }
             qsm[aug + r] = s0 + s1;
         }
-        // ---- U_k: trailing tiles (i, j), k < j <= i, except the chain warp's (k+1, k+1); column-major, round-robin
+        QPB_TICK1(45);                      // right-hand side rows
+        // ---- U_k: trailing tiles (i, j), k < j <= i, except the chain warp's (k+1, k+1); column-major order, dealt
+        // round-robin, four tiles (= four independent DMMA chains) in flight per warp
         {
-            int j = k + 1, p = uw;
+            int j = k + 1, p = (uw == 0) ? nuw : uw;         // (linear index 0 is the chain warp's tile)
             while (j < nts && p >= nts - j) { p -= nts - j; ++j; }
 #pragma unroll 1
             while (j < nts) {
-                const int i1 = j + p, j1 = j;
-                p += nuw;
-                while (j < nts && p >= nts - j) { p -= nts - j; ++j; }
-                const bool two = j < nts;
-                const int i2 = two ? j + p : i1, j2 = two ? j : j1;
-                if (two) {
-                    p += nuw;
-                    while (j < nts && p >= nts - j) { p -= nts - j; ++j; }
+                int ti[4], tj[4];
+                bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ok[u] = j < nts;
+                    ti[u] = ok[u] ? j + p : ti[0];
+                    tj[u] = ok[u] ? j : tj[0];
+                    if (ok[u]) {
+                        p += nuw;
+                        while (j < nts && p >= nts - j) { p -= nts - j; ++j; }
+                    }
                 }
-                const bool act1 = !(i1 == k + 1 && j1 == k + 1);
-                double* c1 = M + pf_rowoff(8 * i1 + g) + 8 * j1 + 2 * q;
-                double* c2 = M + pf_rowoff(8 * i2 + g) + 8 * j2 + 2 * q;
-                const double* pa1 = P + (8 * i1 + g) * kPanLd + q;
-                const double* pb1 = P + (8 * j1 + g) * kPanLd + q;
-                const double* pa2 = P + (8 * i2 + g) * kPanLd + q;
-                const double* pb2 = P + (8 * j2 + g) * kPanLd + q;
-                double2 v1 = *reinterpret_cast<const double2*>(c1);
-                double2 v2 = *reinterpret_cast<const double2*>(c2);
-                const double a10 = pa1[0], a11 = pa1[4], b10 = pb1[0], b11 = pb1[4];
-                const double a20 = pa2[0], a21 = pa2[4], b20 = pb2[0], b21 = pb2[4];
-                if (act1) dmma884(v1.x, v1.y, -a10, b10);
-                if (two) dmma884(v2.x, v2.y, -a20, b20);
-                if (act1) dmma884(v1.x, v1.y, -a11, b11);
-                if (two) dmma884(v2.x, v2.y, -a21, b21);
-                if (act1) *reinterpret_cast<double2*>(c1) = v1;
-                if (two) *reinterpret_cast<double2*>(c2) = v2;
+                double2 v[4];
+                double a0[4], a1[4], b0[4], b1[4];
+                double* cp[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    cp[u] = M + pf_rowoff(8 * ti[u] + g) + 8 * tj[u] + 2 * q;
+                    const double* pa = P + (8 * ti[u] + g) * kPanLd + q;
+                    const double* pb = P + (8 * tj[u] + g) * kPanLd + q;
+                    v[u] = *reinterpret_cast<const double2*>(cp[u]);
+                    a0[u] = pa[0]; a1[u] = pa[4]; b0[u] = pb[0]; b1[u] = pb[4];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ok[u]) dmma884(v[u].x, v[u].y, -a0[u], b0[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ok[u]) dmma884(v[u].x, v[u].y, -a1[u], b1[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ok[u]) *reinterpret_cast<double2*>(cp[u]) = v[u];
             }
         }
+        if (k < 16) QPB_TICK1(48 + k);      // U_k (+ right-hand side rows)
         __syncthreads();
+        QPB_TICK1(44);
     }
 }
 

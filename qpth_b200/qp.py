@@ -55,6 +55,14 @@ STALL_TOL = 1e-6
 # the minimum the latest is returned (1.0 restores the literal rule).
 BEST_TIE = 1.5
 TRACE = False     # keep per-iteration residual traces on st.trace even when verbose != 1 (diagnostics)
+# Kernel choice where a shape has both product-form variants (plan.pf2_ok, e.g. nz = nineq = 100):
+#   "latency"    one QP per SM, W / chol(Q) / factor in shared memory: the shortest time for ONE batch <= #SMs;
+#   "throughput" two QPs per SM (W, chol(Q) read from L2): +23 % QPs/s once the GPU is full (a large batch, or several
+#                batches in flight on several streams), 1.24x the latency of a lone small batch (profiles/r2g_*);
+#   "auto"       throughput when the batch alone exceeds the SM count, else latency.
+# Set qpth_b200.qp.MODE (or QPTH_B200_MODE) before the call; results are identical bit for bit.
+import os as _os
+MODE = _os.environ.get("QPTH_B200_MODE", "auto")
 
 
 class QPSolvers(Enum):
@@ -99,7 +107,10 @@ def solve_forward(Q_, p_, G_, h_, A_, b_, eps=1e-12, verbose=0, notImprovedLim=3
         Q, p, G, h = (_dev64(t, device) for t in (Q_, p_, G_, h_))
         A = _dev64(A_, device) if neq > 0 else None
         b = _dev64(b_, device) if neq > 0 else None
-        plan = _lib.plan_for(nz, nineq, neq)
+        # one QP per SM (W, chol(Q) and the factor all in shared memory) has the lower latency; two QPs per SM (W and
+        # chol(Q) read from L2) the higher throughput once more QPs are in flight than the GPU has SMs (MODE above)
+        two = MODE == "throughput" or (MODE == "auto" and nBatch > _lib.sm_count(device.index or 0))
+        plan = _lib.plan_for(nz, nineq, neq, two=two)
 
         def stride(t, nd, per):
             return per if (t is not None and t.dim() == nd) else 0

@@ -21,7 +21,7 @@ dev = "cuda:0"
 t = {k: (torch.tensor(v, dtype=torch.float64, device=dev) if v.size else torch.Tensor().to(dev).double()) for k, v in pr.items() if k != "dl"}
 f = QPFunction(verbose=-1, check_Q_spd=False)
 plan = _lib.plan_for(n, m, e)
-print("plan: fast=%d coop=%d" % (plan.fast, plan.coop))
+print("plan: fast=%d coop=%d pf=%d pf_global=%d" % (plan.fast, plan.coop, plan.pf, plan.pf_global))
 f(t["Q"], t["p"], t["G"], t["h"], t["A"], t["b"]); torch.cuda.synchronize()
 iters = f.last_solve().iters.cpu().numpy()
 slow = int(np.argmax(iters))
@@ -45,8 +45,10 @@ names = {0: "make_ctx (TMA staging)", 1: "load vectors", 2: "whiten (+ first K i
          9: "best/exit/aug build", 10: "factor_and_solve tail", 11: "aff step, sigma, rhs", 12: "trsv_fwd (cor)", 13: "trsv_bwd (cor)", 14: "issue_K + combine", 15: "matvec_cols (dx)", 16: "exit: unwhiten + outputs",
          24: "chol: diag tile k+1 update", 26: "chol: (chain) F_k+1 / end of step", 28: "invert16", 32: "chol exit", 33: "trsv_bwd (aff)",
          40: "[warp1] gap", 42: "[warp1] named barrier wait", 44: "[warp1] step barrier wait"}
-tot = sum(buf[i] for i in range(40))
+tot = sum(buf[i] for i in range(40)) + sum(buf[i] for i in range(80, 128))   # thread 0 owns slots 0..39 and 80..127 (per-step Cholesky slots); 40..79 are warp 1's
 print("slowest QP (%d): thread-0 slots sum to %d cycles = %.1f us @1.965 GHz (CTA duration by globaltimer: %.1f us); per iteration %.0f cycles" % (slow, tot, tot / 1965.0, dur[slow], tot / (it + 1)))
+chol_steps = sum(buf[i] for i in range(80, 128))
+print("   per-step Cholesky slots of the chain warp (80..127, table below): %d cyc %5.1f%%   per-iter %7.0f" % (chol_steps, 100.0 * chol_steps / tot, chol_steps / (it + 1)))
 for i in list(range(48)):
     if buf[i]:
         print("%2d %-34s %9d cyc  %5.1f%%   per-iter %7.0f" % (i, names.get(i, "?"), buf[i], 100.0 * buf[i] / tot, buf[i] / (it + 1)))

@@ -57,8 +57,9 @@ EXPECTED_PATH = {
 }
 
 
-# product-form kernels (qp_pf.cuh) by default only where no fast kernel exists: (pf, pf_global)
-EXPECTED_PF = {"band_smem": (1, 0), "band_smem_eq": (1, 0), "c4": (1, 1)}
+# product-form kernels (qp_pf.cuh) are the default wherever they fit: (pf, pf_global)
+EXPECTED_PF = {"c2": (1, 0), "c3": (1, 0), "c5_shard0": (1, 0), "c3_b64": (1, 0), "c4_small": (1, 0),
+               "band_smem": (1, 0), "band_smem_eq": (1, 0), "band_setup": (1, 0), "band_setup_eq": (1, 0), "c4": (1, 1)}
 # cases re-run with QPB200_PF=1 (product-form kernels wherever they fit): every non-tiny kernel family
 PF_CASES = ["c2", "c3_b64", "c4_small", "c5_shard0", "band_setup", "band_setup_eq", "band_smem_eq", "c4"]
 
@@ -95,35 +96,43 @@ def test_matches_reference_golden(name, golden_dir):
         assert plan.tiny == 1 and plan.threads == 32, name
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
 @pytest.mark.parametrize("name", PF_CASES)
-def test_product_form_kernels_match_golden(name, golden_dir, monkeypatch):
-    """The product-form / staircase kernels (plan.pf) forced on every shape they support, against the real reference."""
-    from qpth_b200 import _lib
+def test_product_form_kernels_match_golden(name, mode, golden_dir, monkeypatch):
+    """The product-form / staircase kernels (plan.pf) forced on every shape they support, against the real reference.
+    mode 2: additionally the two-QPs-per-SM variant (W and chol(Q) read from L2) wherever it fits."""
+    from qpth_b200 import _lib, qp as qpmod
     monkeypatch.setenv("QPB200_PF", "1")
+    monkeypatch.setattr(qpmod, "MODE", "throughput" if mode == "2" else "latency")
     prob, gold, full = load_case(name, golden_dir)
     Qs, Gs, As = np.asarray(prob["Q"]), np.asarray(prob["G"]), np.asarray(prob["A"])
-    plan = _lib.plan_for(Qs.shape[-1], Gs.shape[-2], As.shape[-2] if As.size else 0)
+    plan = _lib.plan_for(Qs.shape[-1], Gs.shape[-2], As.shape[-2] if As.size else 0, two=(mode == "2"))
     assert plan.pf == 1, name
+    if mode == "2" and name in ("c2", "c3_b64", "c5_shard0", "c4_small"):
+        assert (plan.pf2_ok, plan.pf_two) == (1, 1), name
     out = _run(prob)
-    errs = check_against_golden(out, gold, full, what=name + "[pf]", prob=prob)
-    _report(name + "[pf]", errs)
+    errs = check_against_golden(out, gold, full, what=name + "[pf%s]" % mode, prob=prob)
+    _report(name + "[pf%s]" % mode, errs)
 
 
 @pytest.mark.parametrize("name", SWEEP)
-def test_randomised_sweep_product_form(name, golden_dir, monkeypatch):
-    """The randomised sweep (ill-conditioned Q, wide range of d) through the product-form kernels."""
-    from qpth_b200 import _lib
+def test_randomised_sweep_two_per_sm(name, golden_dir, monkeypatch):
+    """The randomised sweep (ill-conditioned Q, wide range of d) through the two-QPs-per-SM product-form kernels
+    (the default run of the sweep below takes the one-QP-per-SM ones: these batches are smaller than the GPU)."""
+    from qpth_b200 import _lib, qp as qpmod
     from tests.parity import check_sweep
-    monkeypatch.setenv("QPB200_PF", "1")
+    monkeypatch.setattr(qpmod, "MODE", "throughput")
     prob, gold, full = load_case(name, golden_dir)
     Qs, Gs, As = np.asarray(prob["Q"]), np.asarray(prob["G"]), np.asarray(prob["A"])
-    plan = _lib.plan_for(Qs.shape[-1], Gs.shape[-2], As.shape[-2] if As.size else 0)
+    plan = _lib.plan_for(Qs.shape[-1], Gs.shape[-2], As.shape[-2] if As.size else 0, two=True)
     if plan.tiny:
         pytest.skip("one-warp-per-QP shape: no product-form kernel")
     assert plan.pf == 1, name
+    if not plan.pf2_ok:
+        pytest.skip("no two-per-SM variant for this shape")
     out = _run(prob)
-    r = check_sweep(out, prob, gold, what=name + "[pf]")
-    _report(name + "[pf]", {k: v for k, v in r.items() if k in ("z", "dQ", "dp", "dG", "dh", "dA", "db", "ref_kkt", "our_kkt")})
+    r = check_sweep(out, prob, gold, what=name + "[pf2]")
+    _report(name + "[pf2]", {k: v for k, v in r.items() if k in ("z", "dQ", "dp", "dG", "dh", "dA", "db", "ref_kkt", "our_kkt")})
 
 
 @pytest.mark.parametrize("name", SWEEP)
@@ -140,26 +149,36 @@ def test_randomised_sweep_vs_reference(name, golden_dir):
                "iters_max": int(out["iters"].max())})
 
 
-@pytest.mark.parametrize("coop", [0, 1])
-def test_both_solve_kernel_families_agree(coop):
-    """plan.coop selects the co-resident kernels (two QPs per SM, W and chol(Q) read from L2) or the
-    one-QP-per-SM kernels (everything staged in shared memory): same arithmetic, same results."""
-    from qpth_b200 import _lib
+@pytest.mark.parametrize("family", ["pf_one", "pf_two", "r1_fast", "r1_coop"])
+def test_all_solve_kernel_families_agree(family, monkeypatch):
+    """The four kernel families a C2-sized problem can take - product form with one or two QPs per SM (the shipped
+    ones), and the round-1 kernels (QPB200_PF=0: everything staged in shared memory, or co-resident) - against the
+    oracle; the two product-form variants differ only in the summation order of the W / L passes (shared memory vs L2
+    reads) and must agree to 1e-10."""
+    from qpth_b200 import _lib, qp as qpmod
     pr = random_qp_batch(64, 100, 100, 0, seed=17)
-    plan = _lib.plan_for(100, 100, 0)
-    assert plan.coop_ok == 1
-    saved = plan.coop
-    try:
-        plan.coop = coop
-        out = _run(pr)
-    finally:
-        plan.coop = saved
+    if family.startswith("r1"):
+        monkeypatch.setenv("QPB200_PF", "0")
+        monkeypatch.setenv("QPB200_COOP", "1" if family == "r1_coop" else "0")
+        plan = _lib.plan_for(100, 100, 0, two=False)
+        assert plan.pf == 0 and plan.fast == 1 and plan.coop_ok == 1
+    else:
+        monkeypatch.setattr(qpmod, "MODE", "throughput" if family == "pf_two" else "latency")
+        plan = _lib.plan_for(100, 100, 0, two=(family == "pf_two"))
+        assert plan.pf == 1 and plan.pf2_ok == 1 and plan.pf_two == (1 if family == "pf_two" else 0)
+    out = _run(pr)
     ref = orc.qp_solve(pr["Q"][:16], pr["p"][:16], pr["G"][:16], pr["h"][:16], pr["A"][:16], pr["b"][:16],
                        pr["dl"][:16], per_qp=True)
     assert rel_rows(out["zhat"][:16], ref["zhat"]).max() <= ZTOL
     for g, r in zip(out["grads"], ref["grads"]):
         if r is not None:
             assert rel_rows(g[:16], r, floor=1e-4).max() <= GTOL
+    if family == "pf_two":
+        monkeypatch.setattr(qpmod, "MODE", "latency")
+        one = _run(pr)
+        assert rel_rows(one["zhat"], out["zhat"]).max() <= 1e-10
+        for a, b_ in zip(one["grads"], out["grads"]):
+            assert (a is None and b_ is None) or rel_rows(a, b_, floor=1e-4).max() <= 1e-8
 
 
 @pytest.mark.parametrize("cfg", [dict(nBatch=128, nz=100, nineq=100, neq=0),
@@ -277,14 +296,24 @@ def test_pre_factor_blocks_match_definition():
     Q, G, A = tt(pr["Q"]), tt(pr["G"]), tt(pr["A"])
     L = torch.empty(B, plan.L_elems, dtype=torch.float64, device=DEV)
     W = torch.empty(B, plan.ms, plan.ldw, dtype=torch.float64, device=DEV)
-    K = torch.empty(B, plan.ms_pad, plan.lds, dtype=torch.float64, device=DEV)
+    K = torch.empty(B, plan.K_elems, dtype=torch.float64, device=DEV)
     spd = torch.zeros(B, dtype=torch.int32, device=DEV)
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     _lib.check(lib.qpb200_pre_factor_kkt(ctypes.byref(plan), B, P(Q), n * n, P(G), m * n, P(A), e * n,
                                          P(L), P(W), P(K), P(spd), None, st))
     torch.cuda.synchronize()
-    Lp, Wn, Kn = L.cpu().numpy(), W.cpu().numpy()[:, :, :n], K.cpu().numpy()[:, :, :plan.ms]
+    Lp, Wn = L.cpu().numpy(), W.cpu().numpy()[:, :, :n]
+    if plan.pf:      # staircase layout (qp_pf.cuh): element (r, c) at (32 i + 64) i + (r % 8)(8 i + 12) + c, i = r // 8
+        Kf = K.cpu().numpy()
+        Kn = np.zeros((B, plan.ms_pad, plan.ms_pad))
+        for r in range(plan.ms_pad):
+            i = r // 8
+            off = (32 * i + 64) * i + (r % 8) * (8 * i + 12)
+            Kn[:, r, :8 * i + 8] = Kf[:, off:off + 8 * i + 8]
+        Kn = Kn[:, :, :plan.ms]
+    else:
+        Kn = K.cpu().numpy().reshape(B, plan.ms_pad, plan.lds)[:, :, :plan.ms]
     ep = plan.neq_pad
     tri = np.tril_indices(n)
     for i in range(B):
@@ -297,6 +326,18 @@ def test_pre_factor_blocks_match_definition():
         F = orc.Factors(pr["Q"][i:i + 1], pr["G"][i:i + 1], pr["A"][i:i + 1])
         Rk = np.tril(Kn[i][ep:plan.ms, ep:])
         assert np.abs(Rk - np.tril(F.R[0])).max() < 1e-8 * np.abs(F.R[0]).max()
+        if plan.pf:  # equality columns in product form: diagonal tiles T_k = L_kk^-1, below them P_ik = L_ik T_k
+            Wall = np.zeros((plan.ms, n)); Wall[:e] = Wref[:e]; Wall[ep:] = Wref[e:]
+            Sfull = Wall @ Wall.T
+            Sfull[e:ep, e:ep] += np.eye(ep - e)
+            L11 = np.linalg.cholesky(Sfull[:ep, :ep])
+            L21 = np.linalg.solve(L11, Sfull[ep:, :ep].T).T
+            Lfull = np.vstack([L11, L21])
+            for k in range(ep // 8):
+                T = np.linalg.inv(Lfull[8 * k:8 * k + 8, 8 * k:8 * k + 8])
+                assert np.abs(np.tril(Kn[i][8 * k:8 * k + 8, 8 * k:8 * k + 8]) - np.tril(T)).max() < 1e-8 * np.abs(T).max()
+                Pref = Lfull[8 * k + 8:, 8 * k:8 * k + 8] @ T
+                assert np.abs(Kn[i][8 * k + 8:plan.ms, 8 * k:8 * k + 8] - Pref).max() < 1e-8 * max(1.0, np.abs(Pref).max())
 
 
 def test_errors_and_shapes():
