@@ -724,6 +724,8 @@ def main():
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # (prints a banner on stdout: this program's stdout is ONE JSON line)
+            os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local_rank)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     line = run_b200(args, rank, world, local_rank)
