@@ -182,8 +182,17 @@ def e2e_leg(f, dev, rank, world, nsteps_req, warmup, dl):
             for _ in range(NS)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     e = torch.Tensor().to(dev).double()
+    from qpth_b200.util import copy_lower_
+    lower_band = env_int("QPB_BENCH_DQ_BAND", 0)        # 0: read dQ back in full (measured r2j: strips change nothing,
+    q_band = env_int("QPB_BENCH_Q_BAND", 0)             #    the duplex PCIe rate is set by the host -> device direction)
     h2d = sum(v.numel() * 8 for v in hb[0].values())
     d2h = sum(v.numel() * 8 for v in host_out[0].values())
+    if lower_band > 0:
+        strips = sum(min(n, r0 + lower_band) * (min(n, r0 + lower_band) - r0) for r0 in range(0, n, lower_band))
+        d2h += (strips - n * n) * B * 8
+    if q_band > 0:
+        strips = sum(min(n, r0 + q_band) * (min(n, r0 + q_band) - r0) for r0 in range(0, n, q_band))
+        h2d += (strips - n * n) * B * 8
 
     def e2e_step(i):
         j = i % NS
@@ -191,14 +200,21 @@ def e2e_leg(f, dev, rank, world, nsteps_req, warmup, dl):
             src, t, out = hb[j], dbuf[j], host_out[j]
             with torch.no_grad():
                 for k, v in src.items():
-                    t[k].copy_(v, non_blocking=True)                      # H2D
+                    if k == "Q" and q_band > 0:     # Q is symmetric (SPD is a precondition, qp.py:81-85): lower strips only
+                        copy_lower_(t[k], v, band=q_band)
+                    else:
+                        t[k].copy_(v, non_blocking=True)                  # H2D
             for v in t.values():
                 v.grad = None
             z = f(t["Q"], t["p"], t["G"], t["h"], e, e)
             z.backward(dl)
             out["z"].copy_(z.detach(), non_blocking=True)                 # D2H
-            for k, g in (("dQ", "Q"), ("dp", "p"), ("dG", "G"), ("dh", "h")):
+            for k, g in (("dp", "p"), ("dG", "G"), ("dh", "h")):
                 out[k].copy_(t[g].grad, non_blocking=True)
+            if lower_band > 0:      # dQ = 1/2 (dx z^T + z dx^T) is symmetric (qp.py:157-158): its lower triangle comes back
+                copy_lower_(out["dQ"], t["Q"].grad.contiguous(), band=lower_band)
+            else:
+                out["dQ"].copy_(t["Q"].grad, non_blocking=True)
 
     for st_ in streams:
         st_.wait_stream(torch.cuda.current_stream())

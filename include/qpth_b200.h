@@ -155,6 +155,12 @@ int qpb200_qp_host(int device, int nbatch, int nz, int nineq, int neq,
                    double* zhat_host, double* dQ_host, double* dp_host, double* dG_host,
                    double* dh_host, double* dA_host, double* db_host, int* spd_flag_host);
 
+/* Transfer helper for SYMMETRIC (nbatch, n, n) matrices - Q on its way in, dQ on its way out (qp.py:157-158 builds dQ
+ * as 1/2 (dx z^T + z dx^T)): only the lower triangle crosses PCIe, as `band`-row strips (strip b = rows [b band, (b+1)
+ * band) x columns [0, (b+1) band)), one strided 3-D copy per strip on `stream`. The part of the destination above the
+ * strips is left untouched. direction 0: host -> device, 1: device -> host. The host buffer should be pinned. */
+int qpb200_copy_lower(const double* src, double* dst, int nbatch, int n, int band, int direction, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

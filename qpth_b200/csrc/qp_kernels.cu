@@ -2007,4 +2007,27 @@ int qpb200_qp_host(int device, int nbatch, int nz, int nineq, int neq, const dou
     return rc;
 }
 
+// Symmetric matrices (Q, and the gradient dQ = 1/2 (dx z^T + z dx^T), qp.py:157-158) cross PCIe as their lower
+// triangle only: `band`-row strips, strip b = rows [b band, (b+1) band) x columns [0, (b+1) band) of every matrix of the
+// batch, one strided 3-D copy per strip (cudaMemcpy3DAsync; the copy engine walks the pitch). 100 x 100, band 20:
+// 60 % of the bytes. The strictly upper part of the destination (beyond the strips) is left untouched; none of the
+// kernels reads it (Cholesky of Q works on the lower triangle). direction: 0 = host -> device, 1 = device -> host.
+int qpb200_copy_lower(const double* src, double* dst, int nbatch, int n, int band, int direction, void* stream) {
+    if (!src || !dst || nbatch <= 0 || n <= 0 || band <= 0) return QPB200_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int r0 = 0; r0 < n; r0 += band) {
+        const int r1 = (r0 + band < n) ? r0 + band : n;
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof(p));
+        p.srcPtr = make_cudaPitchedPtr((void*)src, (size_t)n * 8, (size_t)n * 8, (size_t)n);
+        p.dstPtr = make_cudaPitchedPtr((void*)dst, (size_t)n * 8, (size_t)n * 8, (size_t)n);
+        p.srcPos = make_cudaPos(0, (size_t)r0, 0);
+        p.dstPos = make_cudaPos(0, (size_t)r0, 0);
+        p.extent = make_cudaExtent((size_t)r1 * 8, (size_t)(r1 - r0), (size_t)nbatch);
+        p.kind = direction ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+        CK(cudaMemcpy3DAsync(&p, st));
+    }
+    return QPB200_OK;
+}
+
 }  // extern "C"

@@ -94,3 +94,21 @@ def to_np(t):
 
 def print_header(msg):
     print('===>', msg)
+
+
+def copy_lower_(dst, src, band=20):
+    """dst[..., lower] = src[..., lower] for a batch of SYMMETRIC matrices (B, n, n), between a (pinned) host tensor
+    and a device tensor, on the current CUDA stream: only the lower triangle crosses PCIe, as `band`-row strips
+    (C ABI `qpb200_copy_lower`). What lies above the strips in `dst` is left as it was. Used for Q on its way to the
+    device and for dQ on its way back (both symmetric: qp.py:81-85 requires an SPD Q, qp.py:157-158 symmetrises dQ)."""
+    import ctypes
+    from . import _lib
+    assert dst.shape == src.shape and dst.dim() == 3 and dst.size(1) == dst.size(2)
+    assert dst.dtype == torch.float64 and src.dtype == torch.float64 and dst.is_contiguous() and src.is_contiguous()
+    assert dst.is_cuda != src.is_cuda, "one side on the host, one on the device"
+    dev = dst.device if dst.is_cuda else src.device
+    with torch.cuda.device(dev):
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.load().qpb200_copy_lower(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()),
+                                                 int(dst.size(0)), int(dst.size(1)), int(band), 1 if src.is_cuda else 0, st))
+    return dst
