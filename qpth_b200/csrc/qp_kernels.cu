@@ -1647,6 +1647,7 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
             plan->pf2_smem_bytes = two_ok ? pf_glb : 0;
             plan->pf_two = (two_ok && want_two) ? 1 : 0;
             plan->K_elems = (int64_t)qpb::pf::pf_elems(msp >> 3);
+            plan->solve_scratch_elems = 0;                   // the factor lives in shared memory: no per-QP global workspace
         }
     }
     return QPB200_OK;
