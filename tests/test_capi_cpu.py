@@ -39,8 +39,14 @@ def test_plan_shapes(lib):
     assert p.solve_smem_bytes <= 232448 and p.ldw % 8 == 4 and p.lds % 8 == 4
     p = _lib.plan_for(50, 50, 10)
     assert (p.neq_pad, p.ms) == (16, 66)
-    p = _lib.plan_for(200, 200, 0)
-    assert p.smem_resident == 0 and p.solve_scratch_elems > 0
+    p = _lib.plan_for(200, 200, 0)         # product-form "large problem" kernels: factor in shared memory, W / L from L2
+    assert p.smem_resident == 0 and (p.pf, p.pf_global, p.pf2_ok) == (1, 1, 0) and p.pf_smem_bytes <= 232448 - 1024
+    assert p.solve_scratch_elems == 0 and p.setup_scratch_elems > 0 and p.K_elems == 32 * 25 * 25 + 64 * 25
+    p = _lib.plan_for(200, 200, 16)        # does not fit any shared-memory variant: global-scratch kernels
+    assert p.pf == 0 and p.solve_scratch_elems > 0
+    p = _lib.plan_for(100, 100, 0)         # both product-form variants; the second one fits twice into an SM
+    assert (p.pf, p.pf_global, p.pf2_ok) == (1, 0, 1) and 2 * (p.pf2_smem_bytes + 1024) <= 232448
+    assert _lib.plan_for(100, 100, 0, two=True).pf_two == 1 and _lib.plan_for(100, 100, 0, two=False).pf_two == 0
     # kernel-family selection (include/qpth_b200.h): co-resident fast kernels at C2/C3, one warp per QP for tiny shapes
     p = _lib.plan_for(100, 100, 0)
     assert (p.fast, p.coop_ok, p.tiny, p.threads) == (1, 1, 0, 256) and 2 * (p.coop_smem_bytes + 1024) <= 232448
