@@ -325,12 +325,12 @@ def run_b200(args, rank, world, local_rank):
             qpmod.MODE = bench_mode
             torch.cuda.synchronize()
     # `value`: K steps with the inputs resident in HBM. A step's kernels have 128 CTAs (one QP each); the GPU holds
-    # 148 (one QP per SM) or 296 (co-resident kernels) at a time and a QP leaves its slot as soon as it has converged
+    # 148 (one QP per SM), 296 or 444 (two / three QPs per SM) at a time and a QP leaves its slot as soon as it has converged
     # (12 Newton iterations on average, 16-18 for the slowest QP of a batch), so a single stream idles most of the
     # machine during the tail of every forward kernel. As in a serving loop (and as in the e2e leg) consecutive steps
     # alternate between INFLIGHT CUDA streams. Every step is still one complete forward + backward over its own
     # batch; the single-stream figure is reported next to it (detail.serial_*).
-    inflight = max(1, env_int("QPB_BENCH_INFLIGHT", 4))
+    inflight = max(1, env_int("QPB_BENCH_INFLIGHT", 6))
     vstreams = [torch.cuda.Stream(device=dev) for _ in range(inflight)]
 
     def timed_window(nsteps, first, streams):
@@ -495,7 +495,7 @@ def run_b200(args, rank, world, local_rank):
                    "mean_newton_iters": iters_mean, "launch": launch_mode, "steps_in_flight": inflight,
                    "serial_ms_per_step": serial_ms / args.steps, "serial_value": total_qps / (serial_ms * 1e-3),
                    "settle_steps": settle_steps, "numa": numa, "mode": bench_mode,
-                   "solve_kernels": ("product form" if plan.pf else "round-1") + (", two QPs per SM (W, chol(Q) from L2)" if (plan.pf and plan.pf_two) else ", one QP per SM"),
+                   "solve_kernels": ("product form" if plan.pf else "round-1") + (", three QPs per SM (192-thread CTAs; W, chol(Q) from L2)" if (plan.pf and plan.pf_three) else ", two QPs per SM (W, chol(Q) from L2)" if (plan.pf and plan.pf_two) else ", one QP per SM"),
                    "serial_kernels": "one QP per SM (latency mode)" if serial_step is not None else "same as value",
                    "kernel_ms_alone": {"setup": setup_ms, "forward": k_ms, "backward": bwd_ms}},
     }

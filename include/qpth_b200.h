@@ -75,6 +75,10 @@ typedef struct qpb200_plan {
                              *    throughput once more QPs are in flight than the GPU has SMs (a large batch, or several
                              *    batches on several streams); one QP per SM has the lower latency for a small batch.      */
     int64_t pf2_smem_bytes; /* dynamic shared memory of the two-QPs-per-SM variant */
+    int pf3_ok;             /* with pf: 1 = a THREE-QPs-per-SM variant exists (192-thread CTAs, <= 76.8 KB per QP)               */
+    int pf_three;           /* with pf3_ok: 1 = use it (takes precedence over pf_two). May be set per call like pf_two.          */
+    int64_t pf3_smem_bytes;
+    int pf_threads;         /* CTA size of the one-QP-per-SM product-form kernels: 256, or 512 for large orders (ms_pad > 128)  */
 } qpb200_plan;
 
 int qpb200_version(void);

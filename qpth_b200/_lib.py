@@ -27,6 +27,7 @@ class Plan(ctypes.Structure):
         ("coop_smem_bytes", ctypes.c_int64), ("coop_ok", ctypes.c_int), ("coop", ctypes.c_int), ("tiny", ctypes.c_int),
         ("pf", ctypes.c_int), ("pf_global", ctypes.c_int), ("pf_smem_bytes", ctypes.c_int64),
         ("pf2_ok", ctypes.c_int), ("pf_two", ctypes.c_int), ("pf2_smem_bytes", ctypes.c_int64),
+        ("pf3_ok", ctypes.c_int), ("pf_three", ctypes.c_int), ("pf3_smem_bytes", ctypes.c_int64), ("pf_threads", ctypes.c_int),
     ]
 
 
@@ -89,19 +90,22 @@ _plans = {}
 
 def plan_for(nz, nineq, neq, two=None):
     """Plan for a shape (cached). `two`: None = the library default; True / False = select / deselect the
-    two-QPs-per-SM variant of the product-form solve kernels when the shape has one (plan.pf2_ok). Every
-    (shape, two) pair has its own Plan object, so concurrent callers never see each other's choice."""
+    several-QPs-per-SM variants of the product-form solve kernels when the shape has them (three per SM if
+    plan.pf3_ok, else two if plan.pf2_ok). Every (shape, two) pair has its own Plan object, so concurrent callers
+    never see each other's choice. QPB200_MAXQPS=2 (development knob) caps the choice at two per SM."""
     # QPB200_PF (development / A-B knob read by qpb200_plan_init: "0" never, "1" product-form kernels wherever they fit,
     # "2" = "1" + the two-QPs-per-SM variant by default)
-    key = (nz, nineq, neq, os.environ.get("QPB200_PF"), None if two is None else bool(two))
+    key = (nz, nineq, neq, os.environ.get("QPB200_PF"), os.environ.get("QPB200_MAXQPS"), os.environ.get("QPB200_NT512"),
+           None if two is None else bool(two))
     if key not in _plans:
         p = Plan()
         rc = load().qpb200_plan_init(nz, nineq, neq, ctypes.byref(p))
         check(rc)
         if os.environ.get("QPB200_COOP") is not None and p.coop_ok:     # development knob: force a kernel family
             p.coop = 1 if os.environ["QPB200_COOP"] == "1" else 0
-        if two is not None and p.pf2_ok:
-            p.pf_two = 1 if two else 0
+        if two is not None:        # throughput mode: as many QPs per SM as the shape has a kernel for
+            p.pf_three = 1 if (two and p.pf3_ok and os.environ.get("QPB200_MAXQPS", "3") == "3") else 0
+            p.pf_two = 1 if (two and p.pf2_ok and not p.pf_three) else 0
         _plans[key] = p
     return _plans[key]
 

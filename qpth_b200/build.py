@@ -5,7 +5,6 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", "qp_kernels.cu")]
 import glob  # noqa: E402
 
 DEPS = sorted(glob.glob(os.path.join(HERE, "csrc", "*"))) + [os.path.join(os.path.dirname(HERE), "include", "qpth_b200.h")]
@@ -26,16 +25,39 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
-        return OUT
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
-           "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-o", OUT] + SRC
+# (source, extra defines, object suffix): the 256-thread build of every kernel + the 192- and 512-thread builds of the
+# product-form solve kernels (three QPs per SM; large orders)
+UNITS = [("qp_kernels.cu", [], "main"),
+         ("qp_alt.cu", ["-DQPB_NT=192", "-DQPB_ALT_CTAS=3"], "alt192"),
+         ("qp_alt.cu", ["-DQPB_NT=512", "-DQPB_ALT_CTAS=1"], "alt512")]
+
+
+def build(force=False, verbose=False, extra=(), out=None):
+    """Compile the three translation units in parallel and link them into one shared library."""
+    out = out or OUT
+    if not force and out == OUT and up_to_date():
+        return out
+    import hashlib
+    import tempfile
+    objdir = os.path.join(tempfile.gettempdir(), "qpth_b200_obj_" + hashlib.sha1(out.encode()).hexdigest()[:10])
+    os.makedirs(objdir, exist_ok=True)
+    base = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+            "-Xcompiler", "-fPIC"] + list(extra)
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
-    return OUT
+        base.insert(1, "-Xptxas=-v")
+    procs, objs = [], []
+    for src, defs, tag in UNITS:
+        obj = os.path.join(objdir, tag + ".o")
+        cmd = base + defs + ["-c", "-o", obj, os.path.join(HERE, "csrc", src)]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((cmd, subprocess.Popen(cmd)))
+        objs.append(obj)
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    subprocess.check_call([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs)
+    return out
 
 
 if __name__ == "__main__":

@@ -131,7 +131,8 @@ __device__ __forceinline__ double tri_norm2_partial(const double* Lp, int n, con
     return acc;
 }
 
-// Block-wide reductions of N values. `red` is shared scratch of >= N * 32 doubles.
+// Block-wide reductions of N values. `red` is shared scratch of >= N * kRedStride doubles (up to 16 warps).
+constexpr int kRedStride = 16;
 // Every thread returns with the reduced values. Two barriers per call.
 template <int N, bool kMin>
 __device__ __forceinline__ void block_reduce(double (&v)[N], double* red, int tid, int nt) {
@@ -141,13 +142,13 @@ __device__ __forceinline__ void block_reduce(double (&v)[N], double* red, int ti
     __syncthreads();   // protect scratch from the previous call's readers
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) red[k * 32 + warp] = v[k];
+        for (int k = 0; k < N; ++k) red[k * kRedStride + warp] = v[k];
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         double a = kMin ? INFINITY : 0.0;
-        for (int w = 0; w < nw; ++w) a = kMin ? fmin(a, red[k * 32 + w]) : a + red[k * 32 + w];
+        for (int w = 0; w < nw; ++w) a = kMin ? fmin(a, red[k * kRedStride + w]) : a + red[k * kRedStride + w];
         v[k] = a;
     }
 }

@@ -51,7 +51,10 @@ __shared__ long long s_tim2;
 #define QPB_TICK1(i) do {} while (0)
 #endif
 
-constexpr int kNT = 256;
+#ifndef QPB_NT
+#define QPB_NT 256       // CTA size of the solve kernels; qp_alt.cu builds the product-form ones at 192 and 512 threads as well
+#endif
+constexpr int kNT = QPB_NT;
 
 // ---- 8x8 diagonal block helpers (always full blocks here) -------------------------------------------
 // Storage convention of a factored diagonal block: strictly-lower part = L, DIAGONAL = 1 / L_cc.
@@ -1002,16 +1005,17 @@ __device__ __noinline__ double f_tri_norm2(int Lp, int n, int x) {
 // per batch). The factors were written by the previous launch and are read-only here: ld.global.nc.
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
-// y1 = W x1 (, y2 = W x2). 8 lanes per row (lane j: 16-byte column pairs 2j + 16k), 32 rows per pass, two passes
+// y1 = W x1 (, y2 = W x2). 8 lanes per row (lane j: 16-byte column pairs 2j + 16k), kNT/8 rows per pass, two passes
 // (14 loads) in flight per thread.
 template <bool kTwo>
 __device__ __forceinline__ void g_matvec_rows_impl(const double* __restrict__ Wg, int ld, int rows, int cols, int x1,
                                                    int x2, int y1, int y2) {
     QPB_SMEM;
     const int tid = threadIdx.x, j = tid & 7, rg = tid >> 3;
+    constexpr int kRG = kNT / 8;                             // row groups per pass (8 lanes per row)
 #pragma unroll 1
-    for (int rb = 0; rb < rows; rb += 64) {                  // warp-uniform trip count
-        const int r0 = rb + rg, r1 = r0 + 32;
+    for (int rb = 0; rb < rows; rb += 2 * kRG) {             // warp-uniform trip count
+        const int r0 = rb + rg, r1 = r0 + kRG;
         const bool ok0 = r0 < rows, ok1 = r1 < rows;
         const double* p0 = Wg + (size_t)(ok0 ? r0 : 0) * ld;
         const double* p1 = Wg + (size_t)(ok1 ? r1 : 0) * ld;

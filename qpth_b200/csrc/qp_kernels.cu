@@ -54,44 +54,9 @@ constexpr int kPfDefault = QPB_PF_DEFAULT;
 constexpr int kPfTwoDefault = QPB_PF_TWO_DEFAULT;
 constexpr int kMaxSmem = 232448 - 1024;   // 227 KB opt-in limit per CTA on sm_100, minus static smem slack
 
-struct KDims {
-    int n, m, e, ep, ms, msp;   // msp = ms rounded up to a multiple of 8 (identity padded)
-    int ldw, lds, rows_s, vl;
-    int lp;          // doubles in the packed lower factor L (rounded up to even)
-};
-constexpr int kTabDoubles = 24;   // 96 uint16 tile-table entries for chol_v2
-
-__host__ __device__ inline int ld_for(int c) {
-    int v = c < 4 ? 4 : c;
-    while ((v & 7) != 4) ++v;
-    return v;
-}
-
-// ---- shared-memory vector slots of the solve / backward kernels (each vl doubles)
-enum Vec {
-    V_PT = 0, V_XT, V_RXT, V_S, V_V, V_RV, V_HW, V_C2, V_W, V_WC, V_DSA, V_DS, V_DXT, V_D,
-    V_BXT, V_BS, V_BV, V_HB, V_DINV, V_DINVL, V_AUG, V_T0, V_T1, V_PART /* 4 slots */, V_COUNT = V_PART + 4
-};
-constexpr int kRedDoubles = 4 * 32;
-
-// vector slots + reduction scratch + 2 mbarriers (16 B)
-__host__ __device__ inline size_t solve_vec_doubles(int vl) { return (size_t)V_COUNT * vl + kRedDoubles + 2 + 24; }
-
-// Global-scratch fallback of the K -> S copy (shared-memory mode uses one TMA bulk copy instead).
-__device__ __forceinline__ void copy_K(double* LS, const double* Kg, int total, int tid, int nt) {
-    int i = tid;
-    for (; i + 3 * nt < total; i += 4 * nt) {
-        const double a = Kg[i], b = Kg[i + nt], c = Kg[i + 2 * nt], d = Kg[i + 3 * nt];
-        LS[i] = a; LS[i + nt] = b; LS[i + 2 * nt] = c; LS[i + 3 * nt] = d;
-    }
-    for (; i < total; i += nt) LS[i] = Kg[i];
-}
-
-// get_step (batch.py:210-213) for one QP: min over entries with dv <= 0 of -v/dv;
-// 1.0 when every dv > 0 (the reference's fill value max(1.0, a.max()) at nBatch=1).
-__device__ __forceinline__ double step_candidate(double v, double dv) {
-    return (dv > 0.0) ? INFINITY : (-v / dv);
-}
+}  // namespace
+#include "qp_common.cuh"
+namespace {
 
 // Reduced KKT solve with the current factor (solve_kkt, batch.py:349-372), whitened:
 //   aug (in: -h_full restricted to the S system, already forward-substituted) -> w = S^-1 (-h_full)
@@ -572,10 +537,6 @@ k_forward(KDims D, const double* __restrict__ p, int64_t sp, const double* __res
 // kBackward: the backward pass of QPFunction (qp.py:128-182): d from clamped lam/slacks, rx = dl,
 // other right-hand sides zero, fused gradient outer products for batched inputs.
 // ---------------------------------------------------------------------------------------------
-struct BwdOut {
-    double* dQ; double* dp; double* dG; double* dh; double* dA; double* db;
-    int mQ, mp, mG, mh, mA, mb;      // 1 = mean-reduced elsewhere (skip per-QP write)
-};
 
 template <bool kSmem, bool kV2, bool kBackward, bool kTiny = false>
 __global__ void __launch_bounds__(kTiny ? kTinyThreads : kThreads, kTiny ? kTinyCtasPerSm : 1)
@@ -725,593 +686,9 @@ __global__ void k_mean_vec(int B, int len, const double* __restrict__ u, double 
 }
 
 
-// =============================================================================================
-// FAST PATH (shared-memory resident, padded to 8, compact code): k_forward_fast / k_kkt_fast
-// =============================================================================================
-namespace fk {
-using namespace qpb::fast;
-enum FVec { F_PT = 0, F_XT, F_RXT, F_S, F_V, F_RV, F_HW, F_W, F_DSA, F_DS, F_D, F_BXT, F_BS, F_BV, F_HB,
-            F_DINV, F_DINVL, F_AUG, F_T0, F_T1, F_COUNT };
-
-struct FLayout {              // offsets in doubles into the dynamic shared array
-    int W, LS, Lp, vec, red, bar, tab, pan;
-    int vl;
-};
-__host__ __device__ inline int fast_vl(int n, int msp) { return ((n > msp ? n : msp) + 7) & ~7; }
-// coop = W and packed L are NOT staged (they are read from global memory, qp_fast.cuh). Without pf the packed L
-// visits the S workspace twice (whitening at entry, un-whitening at exit), so Lp aliases LS; with pf the two packed-L
-// substitutions read L straight from global memory and nothing is staged.
-// pf = product-form factor in the staircase layout (qp_pf.cuh): S shrinks to pf_elems, plus the panel scratch.
-__host__ __device__ inline int s_doubles(const KDims& D, bool pf) {
-    return pf ? qpb::pf::pf_elems(D.msp >> 3) : D.msp * D.lds;
-}
-__host__ __device__ inline FLayout fast_layout(const KDims& D, bool coop, bool pf = false) {
-    FLayout L;
-    L.vl = fast_vl(D.n, D.msp);
-    L.W = 0;
-    L.LS = coop ? 0 : L.W + D.ms * D.ldw;
-    L.pan = L.LS + s_doubles(D, pf);
-    const int after_s = L.pan + (pf ? (D.msp + 8) * qpb::pf::kPanLd : 0);
-    L.Lp = coop ? L.LS : after_s;
-    L.vec = coop ? after_s : L.Lp + D.lp;
-    L.red = L.vec + F_COUNT * L.vl;
-    L.bar = L.red + kRedDoubles;
-    L.tab = L.bar + 2;
-    return L;
-}
-__host__ __device__ inline size_t fast_smem_doubles(const KDims& D, bool coop, bool pf = false) {
-    const FLayout L = fast_layout(D, coop, pf);
-    return (size_t)L.tab + kTabDoubles;
-}
-
-struct FCtx {
-    FLayout L;
-    const double* Kg;
-    const double* Wg;     // co-resident mode: W and packed L in global memory
-    const double* Lg;
-    uint32_t kphase;
-    uint32_t lphase;      // parity of the next completion on bar[0] (W/L staging)
-    uint32_t kbytes;      // size of the K template (square or staircase layout)
-    bool kpending;
-};
-#define FV(i) (C.L.vec + (i) * C.L.vl)
-
-__device__ __noinline__ void f_issue_K_impl(int LS, const double* Kg, int bar_off, uint32_t bytes) {
-    QPB_SMEM;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(qsm + bar_off);
-    fence_proxy_async();
-    mbar_expect_tx(bar + 1, bytes);
-    bulk_issue_thread(qsm + LS, Kg, bytes, bar + 1);
-}
-// Call with all threads AFTER a block barrier that retired every reader of the previous factor.
-__device__ __forceinline__ void f_issue_K(const KDims& D, FCtx& C) {
-    if (threadIdx.x == 0) f_issue_K_impl(C.L.LS, C.Kg, C.L.bar, C.kbytes);
-    C.kpending = true;
-}
-__device__ __forceinline__ void f_wait_K(FCtx& C) {
-    QPB_SMEM;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(qsm + C.L.bar);
-    mbar_wait(bar + 1, C.kphase);
-    C.kphase ^= 1u;
-    C.kpending = false;
-}
-
-// Co-resident mode: bring the packed L into the (currently dead) S workspace. Call with all threads after a block
-// barrier that retired every reader of the workspace and with no K copy in flight; returns when L has landed.
-__device__ __forceinline__ void f_stage_L(const KDims& D, FCtx& C) {
-    QPB_SMEM;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(qsm + C.L.bar);
-    if (threadIdx.x == 0) {
-        fence_proxy_async();
-        mbar_expect_tx(bar, (uint32_t)(D.lp * 8));
-        bulk_issue_thread(qsm + C.L.Lp, C.Lg, (uint32_t)(D.lp * 8), bar);
-    }
-    mbar_wait(bar, C.lphase);
-    C.lphase ^= 1u;
-}
-
-// Stage W and packed L with TMA, start the first K copy, build the tile table.
-// kCoop: only L is staged (into the S workspace, for the whitening of the caller's first vector); the caller issues
-// the first K copy itself once it is done with L (f_issue_K after a block barrier).
-template <bool kCoop, bool kPF = false>
-__device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double* Lfac, const double* Wfac,
-                                           const double* Kfac, int sF) {
-    QPB_SMEM;
-    FCtx C;
-    C.L = fast_layout(D, kCoop, kPF);
-    const int64_t sys = sF ? qp : 0;
-    C.kbytes = (uint32_t)(s_doubles(D, kPF) * 8);
-    C.Lg = Lfac + sys * (int64_t)D.lp;
-    C.Wg = Wfac + sys * (int64_t)D.ms * D.ldw;
-    C.Kg = Kfac + sys * (int64_t)s_doubles(D, kPF);
-    C.kphase = 0;
-    C.lphase = 0;
-    C.kpending = false;
-    const int tid = threadIdx.x;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(qsm + C.L.bar);
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_init(bar + 1, 1);
-    }
-    if (!kPF) build_tile_table(reinterpret_cast<uint16_t*>(qsm + C.L.tab), (D.msp - D.ep) >> 3, tid);
-    __syncthreads();
-    if (kCoop && kPF) {
-        f_issue_K(D, C);                                         // nothing is staged: L is read from global memory
-        _Pragma("unroll 1") for (int i = tid; i < D.n; i += kNT) qsm[FV(F_DINVL) + i] = 1.0 / C.Lg[(i * (i + 1)) / 2 + i];
-        return C;
-    }
-    if (kCoop) {
-        f_stage_L(D, C);
-    } else {
-        if (tid == 0) {
-            const uint32_t wb = (uint32_t)(D.ms * D.ldw * 8), lb = (uint32_t)(D.lp * 8);
-            mbar_expect_tx(bar, wb + lb);
-            bulk_issue_thread(qsm + C.L.W, C.Wg, wb, bar);
-            bulk_issue_thread(qsm + C.L.Lp, C.Lg, lb, bar);
-        }
-        f_issue_K(D, C);
-        mbar_wait(bar, 0);
-    }
-    // reciprocal diagonals of L (packed) and of the pre-factored equality block
-    _Pragma("unroll 1") for (int i = tid; i < D.n; i += kNT) qsm[FV(F_DINVL) + i] = 1.0 / qsm[C.L.Lp + (i * (i + 1)) / 2 + i];
-    return C;
-}
-
-// x~ = L^-1 x and x = L^-T x~ with the packed L in shared memory, or (global W/L + product form) straight from global
-template <bool kGlobalL>
-__device__ __forceinline__ void f_whiten_x(const KDims& D, const FCtx& C, int b, int u) {
-    QPB_SMEM;
-    if (kGlobalL) trsv_fwd(C.Lg, PackedIdx{}, D.n, 0, D.n, qsm + FV(F_DINVL), qsm + b, qsm + u, (int)threadIdx.x, kNT);
-    else f_whiten(C.L.Lp, D.n, FV(F_DINVL), b, u);
-}
-template <bool kGlobalL>
-__device__ __forceinline__ void f_unwhiten_x(const KDims& D, const FCtx& C, int u, int w) {
-    QPB_SMEM;
-    if (kGlobalL) trsv_bwd(C.Lg, PackedIdx{}, D.n, qsm + FV(F_DINVL), qsm + u, qsm + w, (int)threadIdx.x, kNT);
-    else f_unwhiten(C.L.Lp, D.n, FV(F_DINVL), u, w);
-}
-
-// mat-vec dispatch: shared-memory resident W / L, or the global-memory passes of the co-resident mode
-template <bool kCoop>
-__device__ __forceinline__ void mv_rows1(const KDims& D, const FCtx& C, int x1, int y1) {
-    if (kCoop) g_matvec_rows1(C.Wg, D.ldw, D.ms, D.n, x1, y1);
-    else f_matvec_rows1(C.L.W, D.ldw, D.ms, D.n, x1, y1);
-}
-template <bool kCoop>
-__device__ __forceinline__ void mv_rows2(const KDims& D, const FCtx& C, int x1, int x2, int y1, int y2) {
-    if (kCoop) g_matvec_rows2(C.Wg, D.ldw, D.ms, D.n, x1, x2, y1, y2);
-    else f_matvec_rows2(C.L.W, D.ldw, D.ms, D.n, x1, x2, y1, y2);
-}
-template <bool kCoop>
-__device__ __forceinline__ void mv_cols(const KDims& D, const FCtx& C, int v, int p0, int p1, int out, int a, double sa,
-                                        int b, double sgn) {
-    if (kCoop) g_matvec_cols(C.Wg, D.ldw, D.ms, D.n, v, out, a, sa, b, sgn);
-    else f_matvec_cols(C.L.W, D.ldw, D.ms, D.n, v, p0, p1, out, a, sa, b, sgn);
-}
-
-// factor_kkt + first half of solve_kkt: F_AUG = -h_full (pad entries 0), F_D = d  ->  F_W = -S^-1 h_full
-// pform: rewrite the factor in product form (worth it when two more solves with the same factor follow)
-__device__ __forceinline__ void f_factor_and_solve(const KDims& D, FCtx& C, bool pform) {
-    QPB_SMEM;
-    const int tid = threadIdx.x;
-    f_wait_K(C);
-    _Pragma("unroll 1") for (int i = D.ep + tid; i < D.ms; i += kNT) qsm[C.L.LS + i * D.lds + i] += 1.0 / qsm[FV(F_D) + i];
-    __syncthreads();
-    if (D.ep > 0) {
-        f_trsv_fwd(C.L.LS, D.lds, D.msp, 0, D.ep, FV(F_AUG), FV(F_T0));
-        _Pragma("unroll 1") for (int i = tid; i < D.ep; i += kNT) qsm[FV(F_AUG) + i] = qsm[FV(F_T0) + i];
-        __syncthreads();
-    }
-    f_chol(C.L.LS, D.lds, D.msp, D.ep, FV(F_AUG), C.L.tab);
-    QPB_TICK(32);   // (chol internals are 20..27)
-#if QPB_PFORM
-    if (pform) {
-        f_to_pform(C.L.LS, D.lds, D.msp);                      // T_k, P_ik: every later solve is chain-free
-        QPB_TICK(28);   // product-form conversion
-        f_ptrsv_bwd(C.L.LS, D.lds, D.msp, FV(F_AUG), FV(F_W));
-    } else
-#endif
-    {
-#if QPB_TRSV16
-        f_invert16(C.L.LS, D.lds, D.msp);
-        __syncthreads();
-        QPB_TICK(28);   // inverted 16 x 16 diagonal blocks
-        f_trsv16_bwd(C.L.LS, D.lds, D.msp, FV(F_AUG), FV(F_W), C.L.red);
-#else
-        f_trsv_bwd(C.L.LS, D.lds, D.msp, FV(F_AUG), FV(F_W));
-#endif
-    }
-    QPB_TICK(33);   // backward substitution
-}
-
-// The same with the product-form factor (qp_pf.cuh): F_AUG = -h_full, F_D = d  ->  F_W = -S^-1 h_full; F_T0 scratch.
-__device__ __forceinline__ void f_factor_and_solve_pf(const KDims& D, FCtx& C) {
-    QPB_SMEM;
-    using namespace qpb::pf;
-    const int tid = threadIdx.x;
-    f_wait_K(C);
-    _Pragma("unroll 1") for (int i = D.ep + tid; i < D.ms; i += kNT) qsm[C.L.LS + pf_rowoff(i) + i] += 1.0 / qsm[FV(F_D) + i];
-    __syncthreads();
-    if (D.ep > 0) pf_fwd(C.L.LS, D.msp, 0, D.ep >> 3, FV(F_AUG));
-    pf_chol(C.L.LS, D.msp >> 3, D.ep >> 3, FV(F_AUG), C.L.pan);
-    QPB_TICK(32);
-    pf_diag(C.L.LS, D.msp, FV(F_AUG), FV(F_T0), FV(F_AUG));
-    pf_bwd(C.L.LS, D.msp, FV(F_AUG), FV(F_W));
-    QPB_TICK(33);
-}
-
-__device__ __forceinline__ double f_step_fix(double v) { return (isinf(v) && v > 0.0) ? 1.0 : v; }
-
-}  // namespace fk
-
-// kCoop: co-resident mode (two CTAs per SM; W and L read from global memory, see qp_fast.cuh).
-// kPF: product-form factor in the staircase layout (qp_pf.cuh); with kCoop it is the "large problem" kernel: factor
-// and vectors in shared memory, W and L read from global memory (L2-resident when the system is shared), ONE CTA per SM.
-// kTwo (with kCoop && kPF): the same kernel compiled for TWO CTAs per SM (128 registers): 78 KB of shared memory per QP at
-// C2, so two QPs share an SM and fill each other's pivot-chain bubbles.
-template <bool kCoop, bool kPF = false, bool kTwo = false>
-__global__ void __launch_bounds__(kThreads, ((kCoop && !kPF) || kTwo) ? 2 : 1)
-k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* __restrict__ h, int64_t sh,
-               const double* __restrict__ b, int64_t sb, const double* __restrict__ Lfac,
-               const double* __restrict__ Wfac, const double* __restrict__ Kfac, int sF, double eps,
-               double stall_tol, double best_tie, int notImprovedLim, int maxIter,
-               double* __restrict__ zhat, double* __restrict__ lam, double* __restrict__ slacks,
-               double* __restrict__ nus, int* __restrict__ iters_out, double* __restrict__ resid_out,
-               double* __restrict__ trace) {
-    using namespace fk;
-    QPB_SMEM;
-    const int tid = threadIdx.x;
-    const int qp = blockIdx.x;
-    const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
-#ifdef QPB_TIMING
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 128; ++i) s_tim[i] = 0;
-        s_tim[128] = clock64(); s_tim2 = s_tim[128];
-        if (qp < 8192) { g_cta[4 * qp] = gtimer(); g_cta[4 * qp + 3] = smid(); }
-    }
-    __syncthreads();
-#endif
-    FCtx C = f_make_ctx<kCoop, kPF>(D, qp, Lfac, Wfac, Kfac, sF);
-    constexpr bool kGL = kCoop && kPF;                          // packed L read from global memory, nothing staged
-    QPB_TICK(0);
-    const int pt = FV(F_PT), xt = FV(F_XT), rxt = FV(F_RXT), s = FV(F_S), v = FV(F_V), rv = FV(F_RV),
-              hW = FV(F_HW), w = FV(F_W), dsa = FV(F_DSA), ds = FV(F_DS), d = FV(F_D), hb = FV(F_HB),
-              aug = FV(F_AUG), t0 = FV(F_T0), t1 = FV(F_T1);
-
-    const double* pg = p + (int64_t)qp * sp;
-    const double* hg = h + (int64_t)qp * sh;
-    const double* bg = (e > 0) ? (b + (int64_t)qp * sb) : nullptr;
-    _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[t1 + i] = pg[i];
-    _Pragma("unroll 1") for (int i = tid; i < msp; i += kNT) {
-        double val = 0.0;
-        if (i < e) val = bg[i];
-        else if (i >= ep && i < ms) val = hg[i - ep];
-        qsm[hb + i] = val;
-        qsm[d + i] = 1.0;
-        qsm[s + i] = 0.0;
-        qsm[v + i] = 0.0;
-        qsm[aug + i] = 0.0;
-        qsm[w + i] = 0.0;
-    }
-    __syncthreads();
-    QPB_TICK(1);
-    f_whiten_x<kGL>(D, C, t1, pt);                              // p~ = L^-1 p
-    if (kCoop && !kPF) {                                        // L leaves the S workspace: the first K copy may land
-        __syncthreads();
-        f_issue_K(D, C);
-    }
-    QPB_TICK(2);
-
-    // ---- initial point: solve_kkt(p, 0, -h, -b) with d = 1   (batch.py:61-67)
-    mv_rows1<kCoop>(D, C, pt, hW);
-    __syncthreads();
-    _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) qsm[aug + i] = -(qsm[hW + i] + qsm[hb + i]);
-    __syncthreads();
-    if (kPF) f_factor_and_solve_pf(D, C); else f_factor_and_solve(D, C, false);
-    f_issue_K(D, C);
-    mv_cols<kCoop>(D, C, w, t0, t1, xt, pt, -1.0, -1, -1.0);   // x~ = -p~ - W^T w
-    {
-        double mn[2] = {INFINITY, INFINITY};
-        _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) {
-            const double wi = qsm[w + i];
-            qsm[v + i] = wi;
-            if (i >= ep) {
-                qsm[s + i] = -wi;
-                mn[0] = fmin(mn[0], -wi);
-                mn[1] = fmin(mn[1], wi);
-            }
-        }
-        f_reduce_min2(mn, C.L.red);
-        _Pragma("unroll 1") for (int i = ep + tid; i < ms; i += kNT) {               // slacks and duals >= 1 (batch.py:77-87)
-            if (mn[0] < 0.0) qsm[s + i] -= mn[0] - 1.0;
-            if (mn[1] < 0.0) qsm[v + i] -= mn[1] - 1.0;
-        }
-        __syncthreads();
-    }
-
-    double best = 0.0, ret_resid = 0.0;
-    int nNot = 0, iters_run = 0;
-    const double dm = (double)m;
-    for (int it = 0; it < maxIter; ++it) {
-        iters_run = it + 1;
-        // ---- residuals (batch.py:94-107)
-        QPB_TICK(3);
-        mv_cols<kCoop>(D, C, v, t0, t1, rxt, xt, 1.0, pt, 1.0);      // r~x = x~ + p~ + W^T [y;z]
-        QPB_TICK(4);
-        mv_rows2<kCoop>(D, C, xt, rxt, rv, hW);                      // W x~ , W r~x
-        __syncthreads();
-        QPB_TICK(5);
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};                   // |ry|^2, |rz|^2, |L r~x|^2, s.z
-        _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) {
-            const double r = qsm[rv + i] - qsm[hb + i] + ((i >= ep) ? qsm[s + i] : 0.0);
-            qsm[rv + i] = r;
-            if (i < ep) acc[0] = fma(r, r, acc[0]);
-            else { acc[1] = fma(r, r, acc[1]); acc[3] = fma(qsm[s + i], qsm[v + i], acc[3]); }
-        }
-        QPB_TICK(6);
-        acc[2] = kCoop ? g_tri_norm2(C.Lg, n, rxt) : f_tri_norm2(C.L.Lp, n, rxt);
-        QPB_TICK(7);
-        f_reduce_sum4(acc, C.L.red);
-        QPB_TICK(8);
-        const double mu = fabs(acc[3] / dm);
-        const double resid = sqrt(acc[1]) + sqrt(acc[0]) + sqrt(acc[2]) + dm * mu;
-        if (trace != nullptr && tid == 0) {                     // what verbose=1 prints (batch.py:115-117)
-            double* tr = trace + ((int64_t)qp * maxIter + it) * 4;
-            tr[0] = sqrt(acc[1]) + sqrt(acc[0]); tr[1] = sqrt(acc[2]); tr[2] = mu; tr[3] = resid;
-        }
-        // ---- best-iterate tracking and exit tests (batch.py:118-143), per QP (see k_forward)
-        const bool improved = (it == 0) || (resid < best);
-        if (improved) { best = resid; nNot = 0; } else { ++nNot; }
-        if (improved || resid < best_tie * best) {
-            ret_resid = resid;
-            _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[FV(F_BXT) + i] = qsm[xt + i];
-            _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) { qsm[FV(F_BS) + i] = qsm[s + i]; qsm[FV(F_BV) + i] = qsm[v + i]; }
-        }
-        if ((nNot == notImprovedLim && best < stall_tol) || best < eps || mu > 1e32) break;
-        if (!(resid == resid) || isinf(resid)) break;
-        // ---- factor_kkt with d = z/s and the affine right-hand side (batch.py:109-113,150)
-        _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) {
-            double hfull = qsm[hW + i] - qsm[rv + i];
-            if (i >= ep) {
-                const double di = qsm[v + i] / qsm[s + i];
-                qsm[d + i] = di;
-                hfull += qsm[v + i] / di;
-            }
-            qsm[aug + i] = -hfull;
-        }
-        __syncthreads();
-        QPB_TICK(9);
-        if (kPF) f_factor_and_solve_pf(D, C); else f_factor_and_solve(D, C, true);   // w = [dy_aff; dz_aff]
-        QPB_TICK(10);
-        // ---- affine step length and sigma (batch.py:160-168)
-        double mn[2] = {INFINITY, INFINITY};
-        _Pragma("unroll 1") for (int i = ep + tid; i < ms; i += kNT) {
-            const double dz = qsm[w + i];
-            const double dsi = (-qsm[v + i] - dz) / qsm[d + i];
-            qsm[dsa + i] = dsi;
-            mn[0] = fmin(mn[0], step_candidate(qsm[v + i], dz));
-            mn[1] = fmin(mn[1], step_candidate(qsm[s + i], dsi));
-        }
-        f_reduce_min2(mn, C.L.red);
-        {
-            const double alpha = fmin(fmin(f_step_fix(mn[0]), f_step_fix(mn[1])), 1.0);
-            double sm[2] = {0.0, 0.0};
-            _Pragma("unroll 1") for (int i = ep + tid; i < ms; i += kNT) {
-                sm[0] = fma(qsm[s + i] + alpha * qsm[dsa + i], qsm[v + i] + alpha * qsm[w + i], sm[0]);
-                sm[1] = fma(qsm[s + i], qsm[v + i], sm[1]);
-            }
-            f_reduce_sum2(sm, C.L.red);
-            const double sr = sm[0] / sm[1];
-            const double sig = sr * sr * sr;
-            // ---- corrector right-hand side (batch.py:170-181)
-            _Pragma("unroll 1") for (int i = tid; i < msp; i += kNT) {
-                double rhs = 0.0;
-                if (i >= ep && i < ms) {
-                    const double rsc = (-mu * sig + qsm[dsa + i] * qsm[w + i]) / qsm[s + i];
-                    qsm[ds + i] = rsc;
-                    rhs = -(rsc / qsm[d + i]);
-                }
-                qsm[t1 + i] = rhs;
-            }
-            __syncthreads();
-        }
-        QPB_TICK(11);
-        int wc = t1;                                             // where [dy_cor; dz_cor] lands
-        if (kPF) {
-            qpb::pf::pf_solve(C.L.LS, msp, t1, t0, hW);         // (hW is dead until the combined direction below)
-            wc = hW;
-            QPB_TICK(12);
-        } else {
-#if QPB_PFORM
-        f_ptrsv_fwd(C.L.LS, D.lds, msp, t1, t0);
-        QPB_TICK(12);
-        f_ptrsv_bwd(C.L.LS, D.lds, msp, t0, t1);                 // t1 = [dy_cor; dz_cor]
-#elif QPB_TRSV16
-        f_trsv16_fwd(C.L.LS, D.lds, msp, t1, t0, C.L.red);
-        QPB_TICK(12);
-        f_trsv16_bwd(C.L.LS, D.lds, msp, t0, t1, C.L.red);       // t1 = [dy_cor; dz_cor]
-#else
-        f_trsv_fwd(C.L.LS, D.lds, msp, 0, msp, t1, t0);
-        QPB_TICK(12);
-        f_trsv_bwd(C.L.LS, D.lds, msp, t0, t1);                  // t1 = [dy_cor; dz_cor]
-#endif
-        }
-        QPB_TICK(13);
-        f_issue_K(D, C);                                         // next factor_kkt's K copy overlaps the rest
-        // ---- combined direction, step length, update (batch.py:185-203)
-        mn[0] = INFINITY; mn[1] = INFINITY;
-        _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) {
-            const double wci = qsm[wc + i];
-            const double dv = qsm[w + i] + wci;
-            qsm[w + i] = dv;
-            if (i >= ep) {
-                const double dsc = (-qsm[ds + i] - wci) / qsm[d + i];
-                const double dsi = qsm[dsa + i] + dsc;
-                qsm[ds + i] = dsi;
-                mn[0] = fmin(mn[0], step_candidate(qsm[v + i], dv));
-                mn[1] = fmin(mn[1], step_candidate(qsm[s + i], dsi));
-            }
-        }
-        __syncthreads();
-        QPB_TICK(14);
-        mv_cols<kCoop>(D, C, w, t0, t1, hW, rxt, -1.0, -1, -1.0);     // dx~ = -r~x - W^T dv  (in hW)
-        QPB_TICK(15);
-        f_reduce_min2(mn, C.L.red);
-        {
-            const double alpha = fmin(0.999 * fmin(f_step_fix(mn[0]), f_step_fix(mn[1])), 1.0);
-            _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[xt + i] = fma(alpha, qsm[hW + i], qsm[xt + i]);
-            _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) {
-                qsm[v + i] = fma(alpha, qsm[w + i], qsm[v + i]);
-                if (i >= ep) qsm[s + i] = fma(alpha, qsm[ds + i], qsm[s + i]);
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- outputs: x = L^-T x~_best, y, z, s of the returned iterate (batch.py:205-207)
-    __syncthreads();
-    QPB_TICK(16);
-    if (kCoop && !kPF) {                                         // the S workspace is dead: L comes back for x = L^-T x~
-        if (C.kpending) f_wait_K(C);
-        __syncthreads();
-        f_stage_L(D, C);
-    }
-    f_unwhiten_x<kGL>(D, C, FV(F_BXT), t0);
-    if (C.kpending) f_wait_K(C);                                 // drain the in-flight copy before exit
-    _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) zhat[(int64_t)qp * n + i] = qsm[t0 + i];
-    _Pragma("unroll 1") for (int i = tid; i < m; i += kNT) {
-        lam[(int64_t)qp * m + i] = qsm[FV(F_BV) + ep + i];
-        slacks[(int64_t)qp * m + i] = qsm[FV(F_BS) + ep + i];
-    }
-    if (e > 0 && nus != nullptr)
-        _Pragma("unroll 1") for (int i = tid; i < e; i += kNT) nus[(int64_t)qp * e + i] = qsm[FV(F_BV) + i];
-    if (tid == 0) {
-        iters_out[qp] = iters_run;
-        resid_out[qp] = ret_resid;
-    }
-#ifdef QPB_TIMING
-    QPB_TICK(16);
-    if (tid == 0 && qp == g_tim_target) for (int i = 0; i < 128; ++i) g_tim[i] = s_tim[i];
-    if (tid == 0 && qp < 8192) { g_cta[4 * qp + 1] = gtimer(); g_cta[4 * qp + 2] = iters_run; }
-#endif
-}
-
-template <bool kBackward, bool kCoop, bool kPF = false, bool kTwo = false>
-__global__ void __launch_bounds__(kThreads, ((kCoop && !kPF) || kTwo) ? 2 : 1)
-k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ rx_in,
-           const double* __restrict__ rs_in, const double* __restrict__ rz_in,
-           const double* __restrict__ ry_in, const double* __restrict__ zhat,
-           const double* __restrict__ lam, const double* __restrict__ slacks,
-           const double* __restrict__ nus, const double* __restrict__ Lfac,
-           const double* __restrict__ Wfac, const double* __restrict__ Kfac, int sF,
-           double* __restrict__ dx_out, double* __restrict__ ds_out, double* __restrict__ dz_out,
-           double* __restrict__ dy_out, BwdOut O) {
-    using namespace fk;
-    QPB_SMEM;
-    const int tid = threadIdx.x;
-    const int qp = blockIdx.x;
-    const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
-    FCtx C = f_make_ctx<kCoop, kPF>(D, qp, Lfac, Wfac, Kfac, sF);
-    constexpr bool kGL = kCoop && kPF;
-    const int t = FV(F_PT), d = FV(F_D), hW = FV(F_HW), aug = FV(F_AUG), w = FV(F_W), t0 = FV(F_T0),
-              t1 = FV(F_T1), rsv = FV(F_S), c2 = FV(F_RV), dxt = FV(F_RXT), dxo = FV(F_XT);
-    _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[t1 + i] = rx_in[(int64_t)qp * n + i];
-    _Pragma("unroll 1") for (int i = tid; i < msp; i += kNT) {
-        double di = 1.0, extra = 0.0, rsi = 0.0;
-        if (i >= ep && i < ms) {
-            const int j = i - ep;
-            if (kBackward) {
-                di = fmax(lam[(int64_t)qp * m + j], 1e-8) / fmax(slacks[(int64_t)qp * m + j], 1e-8);   // qp.py:148
-            } else {
-                di = d_in[(int64_t)qp * m + j];
-                rsi = rs_in[(int64_t)qp * m + j];
-                extra = rsi / di - rz_in[(int64_t)qp * m + j];
-            }
-        } else if (!kBackward && i < e) {
-            extra = -ry_in[(int64_t)qp * e + i];
-        }
-        qsm[d + i] = di;
-        qsm[rsv + i] = rsi;
-        qsm[hW + i] = extra;
-        qsm[aug + i] = 0.0;
-    }
-    __syncthreads();
-    f_whiten_x<kGL>(D, C, t1, t);                               // t = L^-1 rx
-    if (kCoop && !kPF) {
-        __syncthreads();
-        f_issue_K(D, C);
-    }
-    mv_rows1<kCoop>(D, C, t, c2);
-    __syncthreads();
-    _Pragma("unroll 1") for (int i = tid; i < ms; i += kNT) qsm[aug + i] = -(qsm[c2 + i] + qsm[hW + i]);
-    __syncthreads();
-    if (kPF) f_factor_and_solve_pf(D, C); else f_factor_and_solve(D, C, false);   // w = [dy; dz]
-    mv_cols<kCoop>(D, C, w, t0, t1, dxt, t, -1.0, -1, -1.0);
-    if (kCoop && !kPF) f_stage_L(D, C);                         // (mv_cols ended with a block barrier; no K copy in flight)
-    f_unwhiten_x<kGL>(D, C, dxt, dxo);                          // dx = L^-T dx~
-    _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) dx_out[(int64_t)qp * n + i] = qsm[dxo + i];
-    _Pragma("unroll 1") for (int i = tid; i < m; i += kNT) {
-        dz_out[(int64_t)qp * m + i] = qsm[w + ep + i];
-        if (!kBackward) ds_out[(int64_t)qp * m + i] = (-qsm[rsv + ep + i] - qsm[w + ep + i]) / qsm[d + ep + i];
-    }
-    if (e > 0 && dy_out != nullptr)
-        _Pragma("unroll 1") for (int i = tid; i < e; i += kNT) dy_out[(int64_t)qp * e + i] = qsm[w + i];
-    if (!kBackward) return;
-
-    // ---- gradients for batched inputs (qp.py:157-176); 128-bit coalesced stores
-    const int zs = FV(F_BXT), ls = FV(F_BV);
-    _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[zs + i] = zhat[(int64_t)qp * n + i];
-    _Pragma("unroll 1") for (int i = tid; i < m; i += kNT) qsm[ls + ep + i] = lam[(int64_t)qp * m + i];
-    _Pragma("unroll 1") for (int i = tid; i < e; i += kNT) qsm[ls + i] = nus[(int64_t)qp * e + i];
-    __syncthreads();
-    if (O.dp && !O.mp) for (int i = tid; i < n; i += kNT) O.dp[(int64_t)qp * n + i] = qsm[dxo + i];
-    if (O.dh && !O.mh) for (int i = tid; i < m; i += kNT) O.dh[(int64_t)qp * m + i] = -qsm[w + ep + i];
-    if (O.db && !O.mb && e > 0) for (int i = tid; i < e; i += kNT) O.db[(int64_t)qp * e + i] = -qsm[w + i];
-    const bool even = (n & 1) == 0;
-    if (O.dQ && !O.mQ) {
-        double* o = O.dQ + (int64_t)qp * n * n;
-        if (even) {
-            const int n2 = n >> 1;
-            _Pragma("unroll 1") for (int i = tid; i < n * n2; i += kNT) {
-                const int r = i / n2, c = (i - r * n2) * 2;
-                const double dr = qsm[dxo + r], zr = qsm[zs + r];
-                reinterpret_cast<double2*>(o)[i] = make_double2(0.5 * (dr * qsm[zs + c] + zr * qsm[dxo + c]),
-                                                                0.5 * (dr * qsm[zs + c + 1] + zr * qsm[dxo + c + 1]));
-            }
-        } else {
-            _Pragma("unroll 1") for (int i = tid; i < n * n; i += kNT) {
-                const int r = i / n, c = i - r * n;
-                o[i] = 0.5 * (qsm[dxo + r] * qsm[zs + c] + qsm[zs + r] * qsm[dxo + c]);
-            }
-        }
-    }
-    if (O.dG && !O.mG) {
-        double* o = O.dG + (int64_t)qp * m * n;
-        if (even) {
-            const int n2 = n >> 1;
-            _Pragma("unroll 1") for (int i = tid; i < m * n2; i += kNT) {
-                const int r = i / n2, c = (i - r * n2) * 2;
-                const double wr = qsm[w + ep + r], lr = qsm[ls + ep + r];
-                reinterpret_cast<double2*>(o)[i] = make_double2(wr * qsm[zs + c] + lr * qsm[dxo + c],
-                                                                wr * qsm[zs + c + 1] + lr * qsm[dxo + c + 1]);
-            }
-        } else {
-            _Pragma("unroll 1") for (int i = tid; i < m * n; i += kNT) {
-                const int r = i / n, c = i - r * n;
-                o[i] = qsm[w + ep + r] * qsm[zs + c] + qsm[ls + ep + r] * qsm[dxo + c];
-            }
-        }
-    }
-    if (O.dA && !O.mA && e > 0) {
-        double* o = O.dA + (int64_t)qp * e * n;
-        _Pragma("unroll 1") for (int i = tid; i < e * n; i += kNT) {
-            const int r = i / n, c = i - r * n;
-            o[i] = qsm[w + r] * qsm[zs + c] + qsm[ls + r] * qsm[dxo + c];
-        }
-    }
-}
-
-
+}  // namespace
+#include "qp_solve.cuh"
+namespace {
 // ---------------------------------------------------------------------------------------------
 // k_setup_fast: pre_factor_kkt (batch.py:375-429) with the fast building blocks.
 //   1. chol(Q) with the pipelined f_chol (Q identity-padded to a multiple of 8),
@@ -1541,6 +918,25 @@ int set_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
+// ---- the 192- and 512-thread builds of the product-form solve kernels (qp_alt.cu) ----------------------------------
+extern "C" {
+#define QPB_ALT_DECL(NT)                                                                                                  \
+    int qpb200_alt##NT##_forward(const qpb200_plan*, size_t, int, const double*, int64_t, const double*, int64_t,          \
+                                 const double*, int64_t, const double*, const double*, const double*, int, double, double, \
+                                 double, int, int, double*, double*, double*, double*, int*, double*, double*, void*);     \
+    int qpb200_alt##NT##_solve_kkt(const qpb200_plan*, size_t, int, const double*, const double*, const double*,           \
+                                   const double*, const double*, const double*, const double*, const double*, int,         \
+                                   double*, double*, double*, double*, void*);                                             \
+    int qpb200_alt##NT##_backward(const qpb200_plan*, size_t, int, const double*, const double*, const double*,            \
+                                  const double*, const double*, const double*, const double*, const double*, int, double*, \
+                                  int, double*, int, double*, int, double*, int, double*, int, double*, int, double*,      \
+                                  double*, double*, void*);
+QPB_ALT_DECL(192)
+QPB_ALT_DECL(512)
+#undef QPB_ALT_DECL
+void qpb200_internal_cuda_error(int err, const char* what) { cuda_fail((cudaError_t)err, what); }
+}
+
 extern "C" {
 
 int qpb200_version(void) { return 100; }
@@ -1595,7 +991,7 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
     // CTA per QP is 8 warps synchronising over a handful of rows; one warp per QP and 16 QPs per SM instead
     const bool tiny = kTinyDefault && fits && nz <= kTinyMax && msp <= kTinyMax;
     plan->tiny = tiny ? 1 : 0;
-    plan->pf = 0; plan->pf_global = 0; plan->pf_smem_bytes = 0; plan->pf2_ok = 0; plan->pf2_smem_bytes = 0; plan->pf_two = 0;
+    plan->pf = 0; plan->pf_global = 0; plan->pf_smem_bytes = 0; plan->pf2_ok = 0; plan->pf2_smem_bytes = 0; plan->pf_two = 0; plan->pf3_ok = 0; plan->pf3_smem_bytes = 0; plan->pf_three = 0; plan->pf_threads = 256;
     if (tiny) {
         plan->fast = 0; plan->setup_fast = 0; plan->smem_resident = 1; plan->threads = kTinyThreads;
         plan->setup_smem_bytes = (setup_mat + setup_vec) * 8;
@@ -1635,8 +1031,10 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
         int want = kPfDefault;                               // 0: only where there is no fast kernel; 1: wherever possible
         const char* env = getenv("QPB200_PF");               // development / A-B knob: "0" never, "1" wherever possible,
         if (env != nullptr && env[0] == '0') want = -1;      // "2" = "1" + two QPs per SM (W, L from L2) where that fits
-        if (env != nullptr && (env[0] == '1' || env[0] == '2')) want = 1;
-        const bool two_ok = glb_ok && pf_glb <= (232448 / 2 - 1024 - 64);
+        if (env != nullptr && (env[0] == '1' || env[0] == '2' || env[0] == '3')) want = 1;
+        // co-residency: every CTA also costs the 1 KB the hardware reserves, out of 228 KB per SM
+        const bool two_ok = glb_ok && 2 * (pf_glb + 1024) <= 233472;
+        const bool three_ok = glb_ok && 3 * (pf_glb + 1024) <= 233472 && msp <= 192;   // 192-thread CTAs: one row per thread
         const bool want_two = (env != nullptr && env[0] == '2') || (env == nullptr && kPfTwoDefault);
         const bool use = (want == 1 && (res_ok || glb_ok)) || (want == 0 && !fast_ok && (res_ok || glb_ok));
         if (use) {
@@ -1646,6 +1044,12 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
             plan->pf2_ok = two_ok ? 1 : 0;
             plan->pf2_smem_bytes = two_ok ? pf_glb : 0;
             plan->pf_two = (two_ok && want_two) ? 1 : 0;
+            plan->pf3_ok = three_ok ? 1 : 0;
+            plan->pf3_smem_bytes = three_ok ? pf_glb : 0;
+            plan->pf_three = (three_ok && env != nullptr && env[0] == '3') ? 1 : 0;
+            // large orders (nz = nineq = 200): 15 update warps instead of 7 (the factorization is update-bound there)
+            const char* e512 = getenv("QPB200_NT512");
+            plan->pf_threads = (plan->pf_global && msp > 128 && !(e512 != nullptr && e512[0] == '0')) ? 512 : 256;
             plan->K_elems = (int64_t)qpb::pf::pf_elems(msp >> 3);
             plan->solve_scratch_elems = 0;                   // the factor lives in shared memory: no per-QP global workspace
         }
@@ -1718,13 +1122,21 @@ int qpb200_forward(const qpb200_plan* plan, int nbatch, const double* p, int64_t
             const size_t sb_ = K2 ? plan->pf2_smem_bytes : plan->pf_smem_bytes;                         \
             int rc = set_smem(k_forward_fast<KG, true, K2>, sb_);                                       \
             if (rc) return rc;                                                                          \
-            k_forward_fast<KG, true, K2><<<nbatch, kThreads, sb_, st>>>(                                \
+            k_forward_fast<KG, true, K2><<<nbatch, qpb::fast::kNT, sb_, st>>>(                                \
                 D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, \
                 maxIter, zhat, lam, slacks, nus, iters, best_resid, trace);                             \
         } while (0)
-        if (plan->pf_two && plan->pf2_ok) QPB_LAUNCH_PF(true, true);
-        else if (plan->pf_global) QPB_LAUNCH_PF(true, false);
-        else QPB_LAUNCH_PF(false, false);
+        if (plan->pf_three && plan->pf3_ok)
+            return qpb200_alt192_forward(plan, (size_t)plan->pf3_smem_bytes, nbatch, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps,
+                                         stall_tol, best_tie, notImprovedLim, maxIter, zhat, lam, slacks, nus, iters, best_resid,
+                                         trace, stream);
+        else if (plan->pf_two && plan->pf2_ok) QPB_LAUNCH_PF(true, 2);
+        else if (plan->pf_global && plan->pf_threads == 512)
+            return qpb200_alt512_forward(plan, (size_t)plan->pf_smem_bytes, nbatch, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps,
+                                         stall_tol, best_tie, notImprovedLim, maxIter, zhat, lam, slacks, nus, iters, best_resid,
+                                         trace, stream);
+        else if (plan->pf_global) QPB_LAUNCH_PF(true, 0);
+        else QPB_LAUNCH_PF(false, 0);
 #undef QPB_LAUNCH_PF
     } else if (plan->fast && plan->coop && plan->coop_ok) {
         int rc = set_smem(k_forward_fast<true>, plan->coop_smem_bytes);
@@ -1779,12 +1191,18 @@ int qpb200_solve_kkt(const qpb200_plan* plan, int nbatch, const double* d, const
             const size_t sb_ = K2 ? plan->pf2_smem_bytes : plan->pf_smem_bytes;                         \
             int rc = set_smem(k_kkt_fast<false, KG, true, K2>, sb_);                                    \
             if (rc) return rc;                                                                          \
-            k_kkt_fast<false, KG, true, K2><<<nbatch, kThreads, sb_, st>>>(                             \
+            k_kkt_fast<false, KG, true, K2><<<nbatch, qpb::fast::kNT, sb_, st>>>(                             \
                 D, d, rx, rs, rz, ry, nullptr, nullptr, nullptr, nullptr, Lfac, Wfac, Kfac, sF, dx, ds, dz, dy, O); \
         } while (0)
-        if (plan->pf_two && plan->pf2_ok) QPB_LAUNCH_PF(true, true);
-        else if (plan->pf_global) QPB_LAUNCH_PF(true, false);
-        else QPB_LAUNCH_PF(false, false);
+        if (plan->pf_three && plan->pf3_ok)
+            return qpb200_alt192_solve_kkt(plan, (size_t)plan->pf3_smem_bytes, nbatch, d, rx, rs, rz, ry, Lfac, Wfac, Kfac, sF, dx, ds,
+                                           dz, dy, stream);
+        else if (plan->pf_two && plan->pf2_ok) QPB_LAUNCH_PF(true, 2);
+        else if (plan->pf_global && plan->pf_threads == 512)
+            return qpb200_alt512_solve_kkt(plan, (size_t)plan->pf_smem_bytes, nbatch, d, rx, rs, rz, ry, Lfac, Wfac, Kfac, sF, dx, ds,
+                                           dz, dy, stream);
+        else if (plan->pf_global) QPB_LAUNCH_PF(true, 0);
+        else QPB_LAUNCH_PF(false, 0);
 #undef QPB_LAUNCH_PF
     } else if (plan->fast && plan->coop && plan->coop_ok) {
         int rc = set_smem(k_kkt_fast<false, true>, plan->coop_smem_bytes);
@@ -1843,13 +1261,23 @@ int qpb200_backward(const qpb200_plan* plan, int nbatch, const double* dl_dzhat,
             const size_t sb_ = K2 ? plan->pf2_smem_bytes : plan->pf_smem_bytes;                         \
             int rc = set_smem(k_kkt_fast<true, KG, true, K2>, sb_);                                     \
             if (rc) return rc;                                                                          \
-            k_kkt_fast<true, KG, true, K2><<<nbatch, kThreads, sb_, st>>>(                              \
+            k_kkt_fast<true, KG, true, K2><<<nbatch, qpb::fast::kNT, sb_, st>>>(                              \
                 D, nullptr, dl_dzhat, nullptr, nullptr, nullptr, zhat, lam, slacks, nus, Lfac, Wfac, Kfac, sF, dxv, \
                 nullptr, dlamv, dnuv, O);                                                               \
         } while (0)
-        if (plan->pf_two && plan->pf2_ok) QPB_LAUNCH_PF(true, true);
-        else if (plan->pf_global) QPB_LAUNCH_PF(true, false);
-        else QPB_LAUNCH_PF(false, false);
+        if (plan->pf_three && plan->pf3_ok) {
+            int rc = qpb200_alt192_backward(plan, (size_t)plan->pf3_smem_bytes, nbatch, dl_dzhat, zhat, lam, slacks, nus, Lfac, Wfac,
+                                            Kfac, sF, dQ, mean_Q, dp, mean_p, dG, mean_G, dh, mean_h, dA, mean_A, db, mean_b, dxv,
+                                            dlamv, dnuv, stream);
+            if (rc) return rc;
+        } else if (plan->pf_two && plan->pf2_ok) QPB_LAUNCH_PF(true, 2);
+        else if (plan->pf_global && plan->pf_threads == 512) {
+            int rc = qpb200_alt512_backward(plan, (size_t)plan->pf_smem_bytes, nbatch, dl_dzhat, zhat, lam, slacks, nus, Lfac, Wfac,
+                                            Kfac, sF, dQ, mean_Q, dp, mean_p, dG, mean_G, dh, mean_h, dA, mean_A, db, mean_b, dxv,
+                                            dlamv, dnuv, stream);
+            if (rc) return rc;
+        } else if (plan->pf_global) QPB_LAUNCH_PF(true, 0);
+        else QPB_LAUNCH_PF(false, 0);
 #undef QPB_LAUNCH_PF
     } else if (plan->fast && plan->coop && plan->coop_ok) {
         int rc = set_smem(k_kkt_fast<true, true>, plan->coop_smem_bytes);

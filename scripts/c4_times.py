@@ -6,7 +6,7 @@ import numpy as np, torch
 from qpth_b200 import _lib, QPFunction
 from qpth_b200.problems import cls_layer_problem
 B, n, m = 64, 200, 200
-lib = _lib.load(); plan = _lib.plan_for(n, m, 0)
+lib = _lib.load(); plan = _lib.plan_for(n, m, 0, two=(None if os.environ.get('QPB_KT_TWO') is None else os.environ['QPB_KT_TWO'] == '1'))
 pr = cls_layer_problem(B, n, m, seed=0); dev = "cuda:0"
 tt = lambda a: torch.tensor(a, dtype=torch.float64, device=dev).contiguous()
 Q, p, G, h = (tt(pr[k]) for k in ("Q", "p", "G", "h"))

@@ -5,7 +5,7 @@ import numpy as np, torch
 from qpth_b200 import _lib
 from qpth_b200.problems import random_qp_batch
 B, n, m, e = [int(x) for x in (sys.argv[1:5] if len(sys.argv) > 4 else (128, 100, 100, 0))]
-lib = _lib.load(); plan = _lib.plan_for(n, m, e)
+lib = _lib.load(); plan = _lib.plan_for(n, m, e, two=(None if os.environ.get('QPB_KT_TWO') is None else os.environ['QPB_KT_TWO'] == '1'))
 pr = random_qp_batch(B, n, m, e, seed=0); dev = "cuda:0"
 tt = lambda a: torch.tensor(a, dtype=torch.float64, device=dev).contiguous()
 Q, p, G, h, A, b = (tt(pr[k]) for k in ("Q", "p", "G", "h", "A", "b"))

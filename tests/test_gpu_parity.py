@@ -96,20 +96,24 @@ def test_matches_reference_golden(name, golden_dir):
         assert plan.tiny == 1 and plan.threads == 32, name
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["1", "2", "3"])
 @pytest.mark.parametrize("name", PF_CASES)
 def test_product_form_kernels_match_golden(name, mode, golden_dir, monkeypatch):
     """The product-form / staircase kernels (plan.pf) forced on every shape they support, against the real reference.
-    mode 2: additionally the two-QPs-per-SM variant (W and chol(Q) read from L2) wherever it fits."""
+    mode 2 / 3: the two- / three-QPs-per-SM variants (W and chol(Q) read from L2; 256- / 192-thread CTAs) where they fit.
+    (c4 runs the 512-thread build of the one-QP-per-SM kernel in every mode.)"""
     from qpth_b200 import _lib, qp as qpmod
     monkeypatch.setenv("QPB200_PF", "1")
-    monkeypatch.setattr(qpmod, "MODE", "throughput" if mode == "2" else "latency")
+    monkeypatch.setenv("QPB200_MAXQPS", "2" if mode == "2" else "3")
+    monkeypatch.setattr(qpmod, "MODE", "latency" if mode == "1" else "throughput")
     prob, gold, full = load_case(name, golden_dir)
     Qs, Gs, As = np.asarray(prob["Q"]), np.asarray(prob["G"]), np.asarray(prob["A"])
-    plan = _lib.plan_for(Qs.shape[-1], Gs.shape[-2], As.shape[-2] if As.size else 0, two=(mode == "2"))
+    plan = _lib.plan_for(Qs.shape[-1], Gs.shape[-2], As.shape[-2] if As.size else 0, two=(mode != "1"))
     assert plan.pf == 1, name
-    if mode == "2" and name in ("c2", "c3_b64", "c5_shard0", "c4_small"):
-        assert (plan.pf2_ok, plan.pf_two) == (1, 1), name
+    if name in ("c2", "c3_b64", "c5_shard0", "c4_small"):
+        assert (plan.pf2_ok, plan.pf3_ok) == (1, 1) and (plan.pf_two, plan.pf_three) == {"1": (0, 0), "2": (1, 0), "3": (0, 1)}[mode], name
+    if name == "c4":
+        assert plan.pf_threads == 512
     out = _run(prob)
     errs = check_against_golden(out, gold, full, what=name + "[pf%s]" % mode, prob=prob)
     _report(name + "[pf%s]" % mode, errs)
@@ -149,10 +153,10 @@ def test_randomised_sweep_vs_reference(name, golden_dir):
                "iters_max": int(out["iters"].max())})
 
 
-@pytest.mark.parametrize("family", ["pf_one", "pf_two", "r1_fast", "r1_coop"])
+@pytest.mark.parametrize("family", ["pf_one", "pf_two", "pf_three", "r1_fast", "r1_coop"])
 def test_all_solve_kernel_families_agree(family, monkeypatch):
-    """The four kernel families a C2-sized problem can take - product form with one or two QPs per SM (the shipped
-    ones), and the round-1 kernels (QPB200_PF=0: everything staged in shared memory, or co-resident) - against the
+    """The five kernel families a C2-sized problem can take - product form with one, two or three QPs per SM (the
+    shipped ones), and the round-1 kernels (QPB200_PF=0: everything staged in shared memory, or co-resident) - against the
     oracle; the two product-form variants differ only in the summation order of the W / L passes (shared memory vs L2
     reads) and must agree to 1e-10."""
     from qpth_b200 import _lib, qp as qpmod
@@ -163,9 +167,11 @@ def test_all_solve_kernel_families_agree(family, monkeypatch):
         plan = _lib.plan_for(100, 100, 0, two=False)
         assert plan.pf == 0 and plan.fast == 1 and plan.coop_ok == 1
     else:
-        monkeypatch.setattr(qpmod, "MODE", "throughput" if family == "pf_two" else "latency")
-        plan = _lib.plan_for(100, 100, 0, two=(family == "pf_two"))
-        assert plan.pf == 1 and plan.pf2_ok == 1 and plan.pf_two == (1 if family == "pf_two" else 0)
+        monkeypatch.setenv("QPB200_MAXQPS", "2" if family == "pf_two" else "3")
+        monkeypatch.setattr(qpmod, "MODE", "latency" if family == "pf_one" else "throughput")
+        plan = _lib.plan_for(100, 100, 0, two=(family != "pf_one"))
+        assert plan.pf == 1 and plan.pf2_ok == 1 and plan.pf3_ok == 1
+        assert (plan.pf_two, plan.pf_three) == {"pf_one": (0, 0), "pf_two": (1, 0), "pf_three": (0, 1)}[family]
     out = _run(pr)
     ref = orc.qp_solve(pr["Q"][:16], pr["p"][:16], pr["G"][:16], pr["h"][:16], pr["A"][:16], pr["b"][:16],
                        pr["dl"][:16], per_qp=True)
@@ -173,7 +179,7 @@ def test_all_solve_kernel_families_agree(family, monkeypatch):
     for g, r in zip(out["grads"], ref["grads"]):
         if r is not None:
             assert rel_rows(g[:16], r, floor=1e-4).max() <= GTOL
-    if family == "pf_two":
+    if family in ("pf_two", "pf_three"):
         monkeypatch.setattr(qpmod, "MODE", "latency")
         one = _run(pr)
         assert rel_rows(one["zhat"], out["zhat"]).max() <= 1e-10
