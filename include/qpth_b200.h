@@ -144,6 +144,25 @@ int qpb200_solve_kkt(const qpb200_plan* plan, int nbatch,
                      double* dx, double* ds, double* dz, double* dy,
                      double* scratch, void* stream);
 
+/* Robust KKT variants of the reference: factor_solve_kkt_reg / solve_kkt_ir (batch.py:244-310) regularise
+ * the KKT matrix - Q~ = Q + eps I, D~ = D + eps I, -eps I in the two constraint blocks - so that a PSD-singular Q or a
+ * rank-deficient A still factors, and recover the accuracy by iterative refinement against the un-regularised residual.
+ * Here the regularised solve is the SAME pair of kernels with reg_eps threaded through: chol(Q + eps I); reduced matrix
+ * W W^T + diag(eps on equality rows, 1/(d + eps) + eps on inequality rows), which is SPD whatever the rank of A. One
+ * pre_factor_kkt_reg serves every refinement step (the reference refactors each time). reg_eps = 0 is the plain call.
+ * The refinement loop itself (residual + correction) is host-side glue: qpth_b200/kkt.py. */
+int qpb200_pre_factor_kkt_reg(const qpb200_plan* plan, int nsys,
+                              const double* Q, int64_t sQ, const double* G, int64_t sG,
+                              const double* A, int64_t sA, double reg_eps,
+                              double* Lfac, double* Wfac, double* Kfac, int* spd_flag,
+                              double* scratch, void* stream);
+int qpb200_solve_kkt_reg(const qpb200_plan* plan, int nbatch,
+                         const double* d, const double* rx, const double* rs,
+                         const double* rz, const double* ry, double reg_eps,
+                         const double* Lfac, const double* Wfac, const double* Kfac, int sF,
+                         double* dx, double* ds, double* dz, double* dy,
+                         double* scratch, void* stream);
+
 /* Measurement aid: launches blocks x threads threads each issuing 8*iters dependent-chain-free fp64 FMAs
  * (2*8*iters*blocks*threads flops); out needs blocks*threads doubles. bench.py times it with CUDA
  * events to obtain the fp64 roofline denominator on the box it runs on. */

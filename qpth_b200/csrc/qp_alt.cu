@@ -33,6 +33,7 @@ KDims alt_dims(const qpb200_plan* p) {
     D.n = p->nz; D.m = p->nineq; D.e = p->neq; D.ep = p->neq_pad; D.ms = p->ms; D.msp = p->ms_pad;
     D.ldw = p->ldw; D.lds = p->lds; D.rows_s = p->rows_s; D.vl = p->vl;
     D.lp = (int)p->L_elems;
+    D.reg = 0.0;
     return D;
 }
 

@@ -9,6 +9,7 @@ struct KDims {
     int n, m, e, ep, ms, msp;   // msp = ms rounded up to a multiple of 8 (identity padded)
     int ldw, lds, rows_s, vl;
     int lp;          // doubles in the packed lower factor L (rounded up to even)
+    double reg;      // regularisation eps of the iterative-refinement KKT variant (batch.py:244-310); 0 on the QPFunction path
 };
 constexpr int kTabDoubles = 24;   // 96 uint16 tile-table entries for chol_v2
 

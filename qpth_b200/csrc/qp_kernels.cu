@@ -109,6 +109,10 @@ k_setup(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __restr
     }
     copy_matrix(RB + ep * ldn, ldn, Gg, n, m, n, tid, nt);
     __syncthreads();
+    if (D.reg > 0.0) {                                       // Q~ = Q + eps I (solve_kkt_ir, batch.py:247-249)
+        for (int i = tid; i < n; i += nt) RA[i * ldn + i] += D.reg;
+        __syncthreads();
+    }
 
     // [Q; Apad; G] -> [L; W]: Cholesky of Q with the constraint rows riding along (W = [A;G] L^-T)
     chol_partial(RA, ldn, n, 0, n, RB, ldn, ms, dinv, &s_flag, tid, nt);
@@ -151,8 +155,9 @@ k_setup(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __restr
                 dmma884(c0, c1, a, b);
             }
             const int cc = 8 * tj + 2 * q;
-            if (rok && cc < ms) RA[rr * ldk + cc] = c0 + ((rr == cc && rr >= e && rr < ep) ? 1.0 : 0.0);
-            if (rok && cc + 1 < ms) RA[rr * ldk + cc + 1] = c1 + ((rr == cc + 1 && rr >= e && rr < ep) ? 1.0 : 0.0);
+            // dummy equality rows: unit diagonal; real ones: + eps in the regularised variant (A Q~^-1 A^T + eps I)
+            if (rok && cc < ms) RA[rr * ldk + cc] = c0 + ((rr == cc && rr >= e && rr < ep) ? 1.0 : ((rr == cc && rr < e) ? D.reg : 0.0));
+            if (rok && cc + 1 < ms) RA[rr * ldk + cc + 1] = c1 + ((rr == cc + 1 && rr >= e && rr < ep) ? 1.0 : ((rr == cc + 1 && rr < e) ? D.reg : 0.0));
         }
     }
     __syncthreads();
@@ -566,9 +571,12 @@ k_solve_kkt(KDims D, const double* __restrict__ d_in, const double* __restrict__
             if (kBackward) {
                 di = fmax(lam[(int64_t)qp * m + j], 1e-8) / fmax(slacks[(int64_t)qp * m + j], 1e-8);   // qp.py:148
             } else {
-                di = d_in[(int64_t)qp * m + j];
+                // regularised variant (D.reg > 0, batch.py:244-310): d~ = d + eps in the complementarity row, and the slot
+                // holds 1 / (1/d~ + eps) because factor_kkt adds the RECIPROCAL of this slot to the diagonal of S
+                const double dt = d_in[(int64_t)qp * m + j] + D.reg;
+                di = (D.reg > 0.0) ? 1.0 / (1.0 / dt + D.reg) : dt;
                 rsi = rs_in[(int64_t)qp * m + j];
-                extra = rsi / di - rz_in[(int64_t)qp * m + j];
+                extra = rsi / dt - rz_in[(int64_t)qp * m + j];
             }
         } else if (!kBackward && i < e) {
             extra = -ry_in[(int64_t)qp * e + i];
@@ -591,7 +599,7 @@ k_solve_kkt(KDims D, const double* __restrict__ d_in, const double* __restrict__
     for (int i = tid; i < n; i += nt) dx_out[(int64_t)qp * n + i] = dx[i];
     for (int i = tid; i < m; i += nt) {
         dz_out[(int64_t)qp * m + i] = w[ep + i];
-        if (!kBackward) ds_out[(int64_t)qp * m + i] = (-rsv[ep + i] - w[ep + i]) / d[ep + i];
+        if (!kBackward) ds_out[(int64_t)qp * m + i] = (-rsv[ep + i] - w[ep + i]) / (d_in[(int64_t)qp * m + i] + D.reg);
     }
     if (e > 0 && dy_out != nullptr)
         for (int i = tid; i < e; i += nt) dy_out[(int64_t)qp * e + i] = w[i];
@@ -771,6 +779,10 @@ k_setup_fast(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __
     for (int i = tid; i < np; i += kThreads) qsm[S.aug + i] = 0.0;
     build_tile_table(reinterpret_cast<uint16_t*>(qsm + S.tab), np >> 3, tid);
     __syncthreads();
+    if (D.reg > 0.0) {                                       // Q~ = Q + eps I (solve_kkt_ir, batch.py:247-249)
+        for (int i = tid; i < n; i += kThreads) qsm[S.QA + i * ldq + i] += D.reg;
+        __syncthreads();
+    }
     QPB_TICK(34);   // staging
     // ---- 1. Q = L L^T
     f_chol(S.QA, ldq, np, 0, S.aug, S.tab);
@@ -825,6 +837,8 @@ k_setup_fast(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __
             // dummy equality rows and pad rows: unit diagonal
             if (rr == cc && ((rr >= e && rr < ep) || rr >= ms)) v0 += 1.0;
             if (rr == cc + 1 && ((rr >= e && rr < ep) || rr >= ms)) v1 += 1.0;
+            if (rr == cc && rr < e) v0 += D.reg;             // regularised variant: A Q~^-1 A^T + eps I
+            if (rr == cc + 1 && rr < e) v1 += D.reg;
             if (cc <= rr) qsm[S.QA + rr * lds + cc] = v0;
             if (cc + 1 <= rr) qsm[S.QA + rr * lds + cc + 1] = v1;
         }
@@ -886,6 +900,7 @@ KDims dims_of(const qpb200_plan* p) {
     D.n = p->nz; D.m = p->nineq; D.e = p->neq; D.ep = p->neq_pad; D.ms = p->ms; D.msp = p->ms_pad;
     D.ldw = p->ldw; D.lds = p->lds; D.rows_s = p->rows_s; D.vl = p->vl;
     D.lp = (int)p->L_elems;
+    D.reg = 0.0;
     return D;
 }
 
@@ -1057,14 +1072,29 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
     return QPB200_OK;
 }
 
+static int pre_factor_impl(const qpb200_plan* plan, int nsys, const double* Q, int64_t sQ,
+                           const double* G, int64_t sG, const double* A, int64_t sA, double* Lfac,
+                           double* Wfac, double* Kfac, int* spd_flag, double* scratch, void* stream, double reg);
 int qpb200_pre_factor_kkt(const qpb200_plan* plan, int nsys, const double* Q, int64_t sQ,
                           const double* G, int64_t sG, const double* A, int64_t sA, double* Lfac,
                           double* Wfac, double* Kfac, int* spd_flag, double* scratch, void* stream) {
+    return pre_factor_impl(plan, nsys, Q, sQ, G, sG, A, sA, Lfac, Wfac, Kfac, spd_flag, scratch, stream, 0.0);
+}
+int qpb200_pre_factor_kkt_reg(const qpb200_plan* plan, int nsys, const double* Q, int64_t sQ,
+                              const double* G, int64_t sG, const double* A, int64_t sA, double reg_eps, double* Lfac,
+                              double* Wfac, double* Kfac, int* spd_flag, double* scratch, void* stream) {
+    if (!(reg_eps >= 0.0)) return QPB200_ERR_BAD_ARG;
+    return pre_factor_impl(plan, nsys, Q, sQ, G, sG, A, sA, Lfac, Wfac, Kfac, spd_flag, scratch, stream, reg_eps);
+}
+static int pre_factor_impl(const qpb200_plan* plan, int nsys, const double* Q, int64_t sQ,
+                           const double* G, int64_t sG, const double* A, int64_t sA, double* Lfac,
+                           double* Wfac, double* Kfac, int* spd_flag, double* scratch, void* stream, double reg) {
     if (!plan || nsys <= 0 || !Q || !Lfac || !Wfac || !Kfac || !spd_flag) return QPB200_ERR_BAD_ARG;
     if (plan->nineq > 0 && !G) return QPB200_ERR_BAD_ARG;
     if (plan->neq > 0 && !A) return QPB200_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     KDims D = dims_of(plan);
+    D.reg = reg;
     if (plan->tiny) {
         int rc = set_smem(k_setup<true, true>, plan->setup_smem_bytes);
         if (rc) return rc;
@@ -1161,15 +1191,36 @@ int qpb200_forward(const qpb200_plan* plan, int nbatch, const double* p, int64_t
     return QPB200_OK;
 }
 
+static int solve_kkt_impl(const qpb200_plan* plan, int nbatch, const double* d, const double* rx,
+                          const double* rs, const double* rz, const double* ry, const double* Lfac,
+                          const double* Wfac, const double* Kfac, int sF, double* dx, double* ds,
+                          double* dz, double* dy, double* scratch, void* stream, double reg);
 int qpb200_solve_kkt(const qpb200_plan* plan, int nbatch, const double* d, const double* rx,
                      const double* rs, const double* rz, const double* ry, const double* Lfac,
                      const double* Wfac, const double* Kfac, int sF, double* dx, double* ds,
                      double* dz, double* dy, double* scratch, void* stream) {
+    return solve_kkt_impl(plan, nbatch, d, rx, rs, rz, ry, Lfac, Wfac, Kfac, sF, dx, ds, dz, dy, scratch, stream, 0.0);
+}
+int qpb200_solve_kkt_reg(const qpb200_plan* plan, int nbatch, const double* d, const double* rx,
+                         const double* rs, const double* rz, const double* ry, double reg_eps, const double* Lfac,
+                         const double* Wfac, const double* Kfac, int sF, double* dx, double* ds,
+                         double* dz, double* dy, double* scratch, void* stream) {
+    if (!plan || !(reg_eps >= 0.0)) return QPB200_ERR_BAD_ARG;
+    qpb200_plan p256 = *plan;            // the regularised variant exists in the 256-thread builds only
+    p256.pf_three = 0;
+    p256.pf_threads = 256;
+    return solve_kkt_impl(&p256, nbatch, d, rx, rs, rz, ry, Lfac, Wfac, Kfac, sF, dx, ds, dz, dy, scratch, stream, reg_eps);
+}
+static int solve_kkt_impl(const qpb200_plan* plan, int nbatch, const double* d, const double* rx,
+                          const double* rs, const double* rz, const double* ry, const double* Lfac,
+                          const double* Wfac, const double* Kfac, int sF, double* dx, double* ds,
+                          double* dz, double* dy, double* scratch, void* stream, double reg) {
     if (!plan || nbatch <= 0 || !d || !rx || !rs || !rz || !Lfac || !Wfac || !Kfac || !dx || !ds || !dz)
         return QPB200_ERR_BAD_ARG;
     if (plan->neq > 0 && (!ry || !dy)) return QPB200_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     KDims D = dims_of(plan);
+    D.reg = reg;
     BwdOut O;
     memset(&O, 0, sizeof(O));
 #define QPB_LAUNCH_KKT(KS, KV, SCR, SCRN)                                                              \

@@ -512,9 +512,12 @@ k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ 
             if (kBackward) {
                 di = fmax(lam[(int64_t)qp * m + j], 1e-8) / fmax(slacks[(int64_t)qp * m + j], 1e-8);   // qp.py:148
             } else {
-                di = d_in[(int64_t)qp * m + j];
+                // regularised variant (D.reg > 0, batch.py:244-310): d~ = d + eps in the complementarity row, and the slot
+                // holds 1 / (1/d~ + eps) because factor_kkt adds the RECIPROCAL of this slot to the diagonal of S
+                const double dt = d_in[(int64_t)qp * m + j] + D.reg;
+                di = (D.reg > 0.0) ? 1.0 / (1.0 / dt + D.reg) : dt;
                 rsi = rs_in[(int64_t)qp * m + j];
-                extra = rsi / di - rz_in[(int64_t)qp * m + j];
+                extra = rsi / dt - rz_in[(int64_t)qp * m + j];
             }
         } else if (!kBackward && i < e) {
             extra = -ry_in[(int64_t)qp * e + i];
@@ -541,7 +544,7 @@ k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ 
     _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) dx_out[(int64_t)qp * n + i] = qsm[dxo + i];
     _Pragma("unroll 1") for (int i = tid; i < m; i += kNT) {
         dz_out[(int64_t)qp * m + i] = qsm[w + ep + i];
-        if (!kBackward) ds_out[(int64_t)qp * m + i] = (-qsm[rsv + ep + i] - qsm[w + ep + i]) / qsm[d + ep + i];
+        if (!kBackward) ds_out[(int64_t)qp * m + i] = (-qsm[rsv + ep + i] - qsm[w + ep + i]) / (d_in[(int64_t)qp * m + i] + D.reg);
     }
     if (e > 0 && dy_out != nullptr)
         _Pragma("unroll 1") for (int i = tid; i < e; i += kNT) dy_out[(int64_t)qp * e + i] = qsm[w + i];
