@@ -46,7 +46,10 @@ def test_plan_shapes(lib):
     assert p.pf == 0 and p.solve_scratch_elems > 0
     p = _lib.plan_for(100, 100, 0)         # both product-form variants; the second one fits twice into an SM
     assert (p.pf, p.pf_global, p.pf2_ok) == (1, 0, 1) and 2 * (p.pf2_smem_bytes + 1024) <= 232448
-    assert _lib.plan_for(100, 100, 0, two=True).pf_two == 1 and _lib.plan_for(100, 100, 0, two=False).pf_two == 0
+    assert 3 * (p.pf3_smem_bytes + 1024) <= 233472 and p.pf3_ok == 1        # ... and the 192-thread build three times
+    pt, pl = _lib.plan_for(100, 100, 0, two=True), _lib.plan_for(100, 100, 0, two=False)
+    assert (pt.pf_three, pt.pf_two) == (1, 0) and (pl.pf_three, pl.pf_two) == (0, 0)
+    assert _lib.plan_for(200, 200, 0).pf_threads == 512 and p.pf_threads == 256
     # kernel-family selection (include/qpth_b200.h): co-resident fast kernels at C2/C3, one warp per QP for tiny shapes
     p = _lib.plan_for(100, 100, 0)
     assert (p.fast, p.coop_ok, p.tiny, p.threads) == (1, 1, 0, 256) and 2 * (p.coop_smem_bytes + 1024) <= 232448
