@@ -733,15 +733,23 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    # stdout of this program is ONE JSON line: everything any library prints on fd 1 meanwhile (NCCL prints its version
+    # banner there at communicator creation) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
         line = run_reference(args, rank, world)
         if line is not None:
-            print(json.dumps(line), flush=True)
+            emit(line)
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # (prints a banner on stdout: this program's stdout is ONE JSON line)
-            os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local_rank)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     line = run_b200(args, rank, world, local_rank)
@@ -749,7 +757,7 @@ def main():
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 if __name__ == "__main__":
