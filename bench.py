@@ -169,11 +169,15 @@ def make_batches(device, seed0, ncopies, pinned_host=False):
     return out
 
 
-def e2e_leg(f, dev, rank, world, nsteps_req, warmup, dl):
+def e2e_leg(f, dev, rank, world, nsteps_req, warmup, dl, graphs=True):
     """The same step through QPFunction with HOST (pinned) buffers, H2D + D2H inside the timed region. NS steps are
-    kept in flight on NS CUDA streams (as a serving loop would). Returns (median ms, windows, ksteps, NS, h2d, d2h)."""
+    kept in flight on NS CUDA streams (as a serving loop would). Returns (median ms, windows, ksteps, NS, h2d, d2h, how).
+    graphs: each stream's step (H2D copies from pinned memory, QPFunction forward, autograd backward, D2H copies) is
+    captured once in a CUDA graph and replayed - the eager Python loop needs 0.54 ms of host time per step, as long as
+    the step takes on the device (scripts/e2e_host.py); the default-options variant reads a flag back per forward and
+    cannot be captured."""
     B, n, m = CFG["nBatch"], CFG["nz"], CFG["nineq"]
-    NS = max(1, env_int("QPB_BENCH_E2E_INFLIGHT", 4))
+    NS = max(1, env_int("QPB_BENCH_E2E_INFLIGHT", 6))
     hb = make_batches(dev, 1000 * rank, NS, pinned_host=True)
     host_out = [{k: torch.empty(s, dtype=torch.float64).pin_memory()
                  for k, s in (("z", (B, n)), ("dQ", (B, n, n)), ("dp", (B, n)), ("dG", (B, m, n)), ("dh", (B, m)))}
@@ -197,6 +201,10 @@ def e2e_leg(f, dev, rank, world, nsteps_req, warmup, dl):
     def e2e_step(i):
         j = i % NS
         with torch.cuda.stream(streams[j]):
+            e2e_body(j)
+
+    def e2e_body(j):
+        if True:
             src, t, out = hb[j], dbuf[j], host_out[j]
             with torch.no_grad():
                 for k, v in src.items():
@@ -220,6 +228,26 @@ def e2e_leg(f, dev, rank, world, nsteps_req, warmup, dl):
         st_.wait_stream(torch.cuda.current_stream())
     ksteps = max(2 * NS, nsteps_req // NS * NS)
     settle(e2e_step, max(4, warmup), 2 * NS)
+    how = "eager"
+    if graphs and os.environ.get("QPB_BENCH_E2E_GRAPHS", "1") == "1":
+        try:
+            torch.cuda.synchronize()
+            cg = []
+            for j in range(NS):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=streams[j]):
+                    e2e_body(j)
+                cg.append(gph)
+            torch.cuda.synchronize()
+
+            def e2e_step(i):                                      # noqa: F811
+                j = i % NS
+                with torch.cuda.stream(streams[j]):
+                    cg[j].replay()
+            how = "cuda_graph per stream (H2D + QPFunction forward + autograd backward + D2H captured once, replayed)"
+        except Exception as exc:                                  # noqa: BLE001
+            sys.stderr.write("bench: e2e graph capture failed (%s); eager loop\n" % str(exc)[:200])
+            torch.cuda.synchronize()
     for i in range(ksteps):                # untimed rehearsal: same run-ahead, same allocation pattern
         e2e_step(i)
     torch.cuda.synchronize()
@@ -243,7 +271,7 @@ def e2e_leg(f, dev, rank, world, nsteps_req, warmup, dl):
         tt = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = float(tt.item())
-    return e2e_ms, windows, ksteps, NS, h2d, d2h
+    return e2e_ms, windows, ksteps, NS, h2d, d2h, how
 
 
 def run_b200(args, rank, world, local_rank):
@@ -387,13 +415,13 @@ def run_b200(args, rank, world, local_rank):
             print(json.dumps({"value": world * B * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps, "e2e": {"value": 0.0},
                               "detail": {"serial_ms_per_step": serial_ms / args.steps, "steps_in_flight": inflight, "mean_newton_iters": iters_mean}}), flush=True)
         return None
-    e2e_ms, windows, ksteps, NS, h2d, d2h = e2e_leg(f, dev, rank, world, args.steps, args.warmup, dl)
+    e2e_ms, windows, ksteps, NS, h2d, d2h, e2e_how = e2e_leg(f, dev, rank, world, args.steps, args.warmup, dl)
     # ... and with the reference's DEFAULT options (check_Q_spd=True, verbose=0): every forward then reads the
     # SPD / inaccurate-solution flags back before it returns (qp.py:81-85, batch.py:205-206), which serialises the host
     e2e_def = None
     if os.environ.get("QPB_BENCH_E2E_DEFAULT", "1") == "1":
         fdef = QPFunction()
-        d_ms, d_windows, d_k, _, _, _ = e2e_leg(fdef, dev, rank, world, args.steps, args.warmup, dl)
+        d_ms, d_windows, d_k, _, _, _, _ = e2e_leg(fdef, dev, rank, world, args.steps, args.warmup, dl, graphs=False)
         e2e_def = {"value": world * B * d_k / (d_ms * 1e-3), "windows_ms": d_windows,
                    "options": "QPFunction() defaults: check_Q_spd=True verbose=0 (one blocking flag read per forward)"}
     c5 = None
@@ -476,7 +504,7 @@ def run_b200(args, rank, world, local_rank):
                 "d2h_bytes_per_step": d2h, "steps": ksteps, "windows_ms": windows, "statistic": "median of 5 windows",
                 "best_window_value": world * B * ksteps / (min(windows) * 1e-3),
                 "api": "qpth_b200.QPFunction(verbose=-1, check_Q_spd=False); per step: H2D of Q,p,G,h from pinned host memory, fwd, bwd, D2H of z* and all gradients; %d steps in flight on %d CUDA streams" % (NS, NS),
-                "steps_in_flight": NS, "default_options": e2e_def},
+                "steps_in_flight": NS, "launch": e2e_how, "default_options": e2e_def},
         "gpu_launches": 3 * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_forward_fast", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

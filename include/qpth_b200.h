@@ -79,6 +79,9 @@ typedef struct qpb200_plan {
     int pf_three;           /* with pf3_ok: 1 = use it (takes precedence over pf_two). May be set per call like pf_two.          */
     int64_t pf3_smem_bytes;
     int pf_threads;         /* CTA size of the one-QP-per-SM product-form kernels: 256, or 512 for large orders (ms_pad > 128)  */
+    int setup_pf;           /* with pf: 1 = pre_factor_kkt runs the product-form setup kernel (two systems per SM at C2; the
+                             *    only shared-memory setup for nz = nineq = 200), 0 = the round-1 setup kernels               */
+    int64_t setup_pf_smem_bytes;
 } qpb200_plan;
 
 int qpb200_version(void);

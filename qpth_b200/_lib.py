@@ -28,6 +28,7 @@ class Plan(ctypes.Structure):
         ("pf", ctypes.c_int), ("pf_global", ctypes.c_int), ("pf_smem_bytes", ctypes.c_int64),
         ("pf2_ok", ctypes.c_int), ("pf_two", ctypes.c_int), ("pf2_smem_bytes", ctypes.c_int64),
         ("pf3_ok", ctypes.c_int), ("pf_three", ctypes.c_int), ("pf3_smem_bytes", ctypes.c_int64), ("pf_threads", ctypes.c_int),
+        ("setup_pf", ctypes.c_int), ("setup_pf_smem_bytes", ctypes.c_int64),
     ]
 
 
@@ -99,6 +100,7 @@ def plan_for(nz, nineq, neq, two=None):
     # QPB200_PF (development / A-B knob read by qpb200_plan_init: "0" never, "1" product-form kernels wherever they fit,
     # "2" = "1" + the two-QPs-per-SM variant by default)
     key = (nz, nineq, neq, os.environ.get("QPB200_PF"), os.environ.get("QPB200_MAXQPS"), os.environ.get("QPB200_NT512"),
+           os.environ.get("QPB200_SETUP_PF"),
            None if two is None else bool(two))
     if key not in _plans:
         p = Plan()

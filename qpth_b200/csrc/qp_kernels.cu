@@ -868,6 +868,165 @@ k_setup_fast(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_setup_pf: pre_factor_kkt (batch.py:375-429) on the product-form machinery, sized to share an SM.
+//   1. lower triangle of Q -> staircase in shared memory; pf_chol factors it IN PRODUCT FORM (T_k, P_ik) and emits the
+//      plain factor L (packed lower, true diagonal) to global memory as its tiles appear;
+//   2. W = [A; 0; G] L^-T one 8-row tile at a time (a warp stages the tile, sweeps the running right-hand side
+//      tile(i) -= tile(k) P_ik^T, finalises tile(k) T_k^T, all DMMA) straight to global memory;
+//   3. K = W W^T (DMMA, operands re-read from L2: W was written by this CTA) into the staircase that held chol(Q);
+//   4. equality block: the first neq_pad columns of K factored in product form by the same pf_chol (kend), K -> global.
+// Shared memory: staircase of order max(nz_pad, ms_pad) + panel scratch + 4 tile buffers: 88 KB at C2 (two systems per
+// SM; k_setup_fast holds Q and W side by side: 181 KB, one per SM), 220 KB at nz = nineq = 200 (where the only other
+// setup kernel works from global scratch on one CTA: 1.03 ms -> see profiles/r2n_*).
+// ---------------------------------------------------------------------------------------------
+namespace fk {
+constexpr int kSetupStage = 4;          // row tiles of [A; G] staged at a time (one warp each); fewer if shared memory is short
+struct PLayout { int SQ, pan, aug, stage, ldt, nts, nstage, total; };
+__host__ __device__ inline PLayout setup_pf_layout(const KDims& D) {
+    PLayout L;
+    const int np = (D.n + 7) & ~7;
+    const int ord = np > D.msp ? np : D.msp;
+    L.nts = ord >> 3;
+    L.SQ = 0;
+    L.pan = qpb::pf::pf_elems(L.nts) - 8 * qpb::pf::kPanLd;   // (its first 8 rows are never touched: overlap the staircase)
+    L.aug = L.pan + (ord + 8) * qpb::pf::kPanLd;
+    L.stage = L.aug + ord;
+    L.ldt = np + 4;
+    const int room = (kMaxSmem / 8 - L.stage) / (8 * L.ldt);
+    L.nstage = room < 1 ? 1 : (room > kSetupStage ? kSetupStage : room);
+    L.total = L.stage + L.nstage * 8 * L.ldt;
+    return L;
+}
+}  // namespace fk
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_setup_pf(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __restrict__ G, int64_t sG,
+           const double* __restrict__ A, int64_t sA, double* __restrict__ Lfac, double* __restrict__ Wfac,
+           double* __restrict__ Kfac, int* __restrict__ spd_flag) {
+    using namespace fk;
+    using namespace qpb::pf;
+    QPB_SMEM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int sys = blockIdx.x;
+    const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
+    const PLayout PL = setup_pf_layout(D);
+    const int np = (n + 7) & ~7, ntq = np >> 3, nts = msp >> 3;
+    const double* Qg = Q + (int64_t)sys * sQ;
+    const double* Gg = G + (int64_t)sys * sG;
+    const double* Ag = (e > 0) ? (A + (int64_t)sys * sA) : nullptr;
+    double* Lg = Lfac + (int64_t)sys * D.lp;
+    double* Wg = Wfac + (int64_t)sys * ms * D.ldw;
+    double* Kg = Kfac + (int64_t)sys * pf_elems(nts);
+    double* SQ = qsm + PL.SQ;
+    __shared__ int s_flag;
+    if (tid == 0) s_flag = 0;
+    // ---- 1. Q (lower triangle, identity padded, + eps I in the regularised variant) -> staircase
+    for (int r = warp; r < np; r += kThreads / 32) {
+        const int off = pf_rowoff(r), len = 8 * (r >> 3) + 8;
+        for (int c = lane; c < len; c += 32) {
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < n && c < n) v = Qg[(int64_t)r * n + c] + ((r == c) ? D.reg : 0.0);
+            SQ[off + c] = v;
+        }
+    }
+    for (int i = tid; i < (PL.nts << 3); i += kThreads) qsm[PL.aug + i] = 0.0;
+    __syncthreads();
+    pf_chol_setup(PL.SQ, ntq, 0, ntq, PL.aug, PL.pan, Lg, n);
+    // SPD check (qp.py:81-85): every reciprocal pivot (diagonal of the T_k) must be a positive finite number
+    for (int i = tid; i < n; i += kThreads) {
+        const double ri = SQ[pf_rowoff(i) + i];
+        if (!(ri > 0.0) || isinf(ri)) s_flag = 1;
+    }
+    if (tid == 0 && (D.lp > n * (n + 1) / 2)) Lg[D.lp - 1] = 0.0;
+    // ---- 2. W = [A; 0; G] L^-T, kSetupStage row tiles at a time (warps 0 .. kSetupStage-1)
+    for (int rt0 = 0; rt0 < nts; rt0 += PL.nstage) {
+        const int rt = rt0 + warp;
+        if (warp < PL.nstage && rt < nts) {
+            double* T = qsm + PL.stage + warp * 8 * PL.ldt;
+            for (int rr = 0; rr < 8; ++rr) {                 // stage the tile: 8 rows of [A; 0; G; 0], zero padded to np columns
+                const int r = 8 * rt + rr;
+                const double* src = nullptr;
+                if (r < e) src = Ag + (int64_t)r * n;
+                else if (r >= ep && r < ms) src = Gg + (int64_t)(r - ep) * n;
+                for (int c = lane; c < np; c += 32) T[rr * PL.ldt + c] = (src != nullptr && c < n) ? src[c] : 0.0;
+            }
+            __syncwarp();
+            const int wrow = 8 * rt + g;                     // this lane's row of W
+            for (int k = 0; k < ntq; ++k) {
+                const int k0 = 8 * k;
+                const double a0 = T[g * PL.ldt + k0 + q], a1 = T[g * PL.ldt + k0 + q + 4];
+                // running right-hand side: tile(i) -= tile(k) P_ik^T  (B[kk][nn] = P_ik[nn][kk]), two tiles in flight
+                for (int i = k + 1; i < ntq; i += 2) {
+                    const bool two = i + 1 < ntq;
+                    const int r1 = pf_rowoff(8 * i + g) + k0 + q, r2 = pf_rowoff(8 * (two ? i + 1 : i) + g) + k0 + q;
+                    double* c1 = T + g * PL.ldt + 8 * i + 2 * q;
+                    double* c2 = T + g * PL.ldt + 8 * (two ? i + 1 : i) + 2 * q;
+                    double2 v1 = *reinterpret_cast<const double2*>(c1);
+                    double2 v2 = *reinterpret_cast<const double2*>(c2);
+                    const double b10 = SQ[r1], b11 = SQ[r1 + 4], b20 = SQ[r2], b21 = SQ[r2 + 4];
+                    dmma884(v1.x, v1.y, -a0, b10);
+                    if (two) dmma884(v2.x, v2.y, -a0, b20);
+                    dmma884(v1.x, v1.y, -a1, b11);
+                    if (two) dmma884(v2.x, v2.y, -a1, b21);
+                    *reinterpret_cast<double2*>(c1) = v1;
+                    if (two) *reinterpret_cast<double2*>(c2) = v2;
+                }
+                // y_k = tile(k) T_k^T  (B[kk][nn] = T_k[nn][kk]) -> W
+                const int rk = pf_rowoff(k0 + g) + k0;
+                const double bT0 = (q <= g) ? SQ[rk + q] : 0.0, bT1 = (q + 4 <= g) ? SQ[rk + q + 4] : 0.0;
+                double d0 = 0.0, d1 = 0.0;
+                dmma884(d0, d1, a0, bT0);
+                dmma884(d0, d1, a1, bT1);
+                if (wrow < ms) {
+                    double* wr = Wg + (int64_t)wrow * D.ldw + k0 + 2 * q;
+                    if (k0 + 2 * q < n) wr[0] = d0;
+                    if (k0 + 2 * q + 1 < n) wr[1] = d1;
+                }
+                __syncwarp();                                // the tiles of block column k+1 are complete before they are read as A
+            }
+            if (wrow < ms && q == 0)
+                for (int c = n; c < D.ldw; ++c) Wg[(int64_t)wrow * D.ldw + c] = 0.0;   // (padding columns of the W layout)
+        }
+    }
+    __syncthreads();                                         // W is in global memory (visible to the block), chol(Q) is dead
+    if (tid == 0) spd_flag[sys] = s_flag;
+    // ---- 3. K = W W^T -> staircase (lower tiles), unit diagonal on dummy / pad rows, + eps on the real equality rows
+    {
+        const int T2 = nts * (nts + 1) / 2;
+        for (int t = warp; t < T2; t += kThreads / 32) {
+            int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while (ti * (ti + 1) / 2 > t) --ti;
+            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+            const int tj = t - ti * (ti + 1) / 2;
+            const int ra = 8 * ti + g, rb = 8 * tj + g;
+            const double* pa = Wg + (int64_t)(ra < ms ? ra : 0) * D.ldw + q;
+            const double* pb = Wg + (int64_t)(rb < ms ? rb : 0) * D.ldw + q;
+            const bool oka = ra < ms, okb = rb < ms;
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;   // two accumulator chains
+            for (int kk = 0; kk < np; kk += 8) {             // (W has ldw >= n + padding zeros up to the next multiple of 4... guard by n)
+                const double x0 = (oka && kk + q < n) ? pa[kk] : 0.0, y0 = (okb && kk + q < n) ? pb[kk] : 0.0;
+                const double x1 = (oka && kk + 4 + q < n) ? pa[kk + 4] : 0.0, y1 = (okb && kk + 4 + q < n) ? pb[kk + 4] : 0.0;
+                dmma884(c0, c1, x0, y0);
+                dmma884(e0, e1, x1, y1);
+            }
+            const int rr = 8 * ti + g, cc = 8 * tj + 2 * q;
+            double v0 = c0 + e0, v1 = c1 + e1;
+            if (rr == cc && ((rr >= e && rr < ep) || rr >= ms)) v0 += 1.0;
+            if (rr == cc + 1 && ((rr >= e && rr < ep) || rr >= ms)) v1 += 1.0;
+            if (rr == cc && rr < e) v0 += D.reg;
+            if (rr == cc + 1 && rr < e) v1 += D.reg;
+            *reinterpret_cast<double2*>(SQ + pf_rowoff(rr) + cc) = make_double2(v0, v1);
+        }
+    }
+    __syncthreads();
+    // ---- 4. equality block in product form (columns [0, ep)), then K -> global
+    if (ep > 0) pf_chol_setup(PL.SQ, nts, 0, ep >> 3, PL.aug, PL.pan, nullptr, 0);
+    __syncthreads();
+    for (int i = tid; i < pf_elems(nts); i += kThreads) Kg[i] = SQ[i];
+}
+
 // fp64 FMA issue-rate probe: 8 independent DFMA chains per thread (roofline denominator for bench.py)
 __global__ void k_dfma_probe(int iters, double* out) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
@@ -1006,7 +1165,7 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
     // CTA per QP is 8 warps synchronising over a handful of rows; one warp per QP and 16 QPs per SM instead
     const bool tiny = kTinyDefault && fits && nz <= kTinyMax && msp <= kTinyMax;
     plan->tiny = tiny ? 1 : 0;
-    plan->pf = 0; plan->pf_global = 0; plan->pf_smem_bytes = 0; plan->pf2_ok = 0; plan->pf2_smem_bytes = 0; plan->pf_two = 0; plan->pf3_ok = 0; plan->pf3_smem_bytes = 0; plan->pf_three = 0; plan->pf_threads = 256;
+    plan->pf = 0; plan->pf_global = 0; plan->pf_smem_bytes = 0; plan->pf2_ok = 0; plan->pf2_smem_bytes = 0; plan->pf_two = 0; plan->pf3_ok = 0; plan->pf3_smem_bytes = 0; plan->pf_three = 0; plan->pf_threads = 256; plan->setup_pf = 0; plan->setup_pf_smem_bytes = 0;
     if (tiny) {
         plan->fast = 0; plan->setup_fast = 0; plan->smem_resident = 1; plan->threads = kTinyThreads;
         plan->setup_smem_bytes = (setup_mat + setup_vec) * 8;
@@ -1067,6 +1226,16 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
             plan->pf_threads = (plan->pf_global && msp > 128 && !(e512 != nullptr && e512[0] == '0')) ? 512 : 256;
             plan->K_elems = (int64_t)qpb::pf::pf_elems(msp >> 3);
             plan->solve_scratch_elems = 0;                   // the factor lives in shared memory: no per-QP global workspace
+            // pre_factor_kkt on the same machinery (k_setup_pf) whenever its shared memory fits
+            const int64_t spf = (int64_t)fk::setup_pf_layout(D).total * 8;
+            // measured (profiles/r2n_setup_pf.txt): 1.7x faster than the global-scratch setup at nz = nineq = 200 (1037 -> 598
+            // us), but SLOWER than k_setup_fast where that exists (C2, B = 8192: 3.65 vs 3.21 ms even at two per SM: the
+            // W sweep runs on 4 warps and K re-reads W from L2) - so it is the default only where there is no fast setup
+            const char* esp = getenv("QPB200_SETUP_PF");     // development / A-B knob: "0" never, "1" wherever it fits
+            const bool want_spf = (esp != nullptr) ? (esp[0] == '1') : !setup_fast_ok;
+            plan->setup_pf = (spf <= kMaxSmem && want_spf) ? 1 : 0;
+            plan->setup_pf_smem_bytes = spf;
+            if (plan->setup_pf) plan->setup_scratch_elems = 0;
         }
     }
     return QPB200_OK;
@@ -1100,6 +1269,10 @@ static int pre_factor_impl(const qpb200_plan* plan, int nsys, const double* Q, i
         if (rc) return rc;
         k_setup<true, true><<<nsys, kTinyThreads, plan->setup_smem_bytes, st>>>(D, Q, sQ, G, sG, A, sA, Lfac, Wfac, Kfac,
                                                                                  spd_flag, nullptr, 0, 0);
+    } else if (plan->pf && plan->setup_pf) {
+        int rc = set_smem(k_setup_pf, plan->setup_pf_smem_bytes);
+        if (rc) return rc;
+        k_setup_pf<<<nsys, kThreads, plan->setup_pf_smem_bytes, st>>>(D, Q, sQ, G, sG, A, sA, Lfac, Wfac, Kfac, spd_flag);
     } else if (plan->setup_fast) {
         int rc = set_smem(k_setup_fast, plan->setup_smem_bytes);
         if (rc) return rc;

@@ -96,7 +96,22 @@ __device__ __forceinline__ void pf_store_lower8(double* M, int r0, int c0, const
 // Roles: warp 0 = the pivot chain (F_k, the tile below it, the next diagonal tile, F_k+1), warps 1.. = panel + trailing
 // update. Named barrier 1: T_k published (chain arrives, update warps wait); named barrier 2: panel complete (chain
 // arrives, update warps wait); one __syncthreads per step. blockDim.x == kNT.
-__device__ __noinline__ void pf_chol_chain(int S, int nts, int kb0, int pan) {
+// kSetup (pre_factor_kkt, k_setup_pf): stop after block column kend - 1 (the trailing block keeps the Schur complement)
+// and, when Lg != nullptr, emit the plain factor L (rows < ln; packed lower, TRUE diagonal) to global memory as it appears.
+__device__ __forceinline__ void pf_emit_diag(double* Lg, int ln, int k, const double (&Lk)[36]) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int R = 8 * k + r;
+        if (R < ln) {
+            double* row = Lg + ((int64_t)R * (R + 1)) / 2 + 8 * k;
+#pragma unroll
+            for (int c = 0; c < r; ++c) row[c] = Lk[QPB_LIDX(r, c)];
+            row[r] = 1.0 / Lk[QPB_LIDX(r, r)];
+        }
+    }
+}
+template <bool kSetup>
+__device__ __noinline__ void pf_chol_chain_t(int S, int nts, int kb0, int kend, int pan, double* Lg, int ln) {
     QPB_SMEM;
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
@@ -107,8 +122,9 @@ __device__ __noinline__ void pf_chol_chain(int S, int nts, int kb0, int pan) {
     __syncwarp();
     pf_factor8(Lk);
     pf_inv8_col(Lk, lane & 7, Tc);
+    if (kSetup && Lg != nullptr && lane == 0) pf_emit_diag(Lg, ln, kb0, Lk);
 #pragma unroll 1
-    for (int k = kb0; k < nts; ++k) {
+    for (int k = kb0; k < (kSetup ? kend : nts); ++k) {
         const int k0 = 8 * k;
         const bool more = k + 1 < nts;
         const int rn = pf_rowoff(k0 + 8 + g);               // this lane's row of block k+1 (only used if `more`)
@@ -142,10 +158,13 @@ __device__ __noinline__ void pf_chol_chain(int S, int nts, int kb0, int pan) {
             *reinterpret_cast<double2*>(M + rn + k0 + 8 + 2 * q) = cv;
             __syncwarp();
             QPB_TICK(24);               // tile below + next diagonal tile
-            pf_load_lower8(M, k0 + 8, k0 + 8, Lk);
-            __syncwarp();
-            pf_factor8(Lk);                                  // F_{k+1}
-            pf_inv8_col(Lk, lane & 7, Tc);                   // T_{k+1}
+            if (!kSetup || k + 1 < kend) {
+                pf_load_lower8(M, k0 + 8, k0 + 8, Lk);
+                __syncwarp();
+                pf_factor8(Lk);                              // F_{k+1}
+                pf_inv8_col(Lk, lane & 7, Tc);               // T_{k+1}
+                if (kSetup && Lg != nullptr && lane == 0) pf_emit_diag(Lg, ln, k + 1, Lk);
+            }
             if (k < 16) QPB_TICK(80 + k);   // F_{k+1}
         } else {
             named_bar_arrive(2, kNT);
@@ -155,7 +174,12 @@ __device__ __noinline__ void pf_chol_chain(int S, int nts, int kb0, int pan) {
     }
 }
 
-__device__ __noinline__ void pf_chol_update(int S, int nts, int kb0, int aug, int pan) {
+__device__ __forceinline__ void pf_chol_chain(int S, int nts, int kb0, int pan) {
+    pf_chol_chain_t<false>(S, nts, kb0, nts, pan, nullptr, 0);
+}
+
+template <bool kSetup>
+__device__ __noinline__ void pf_chol_update_t(int S, int nts, int kb0, int kend, int aug, int pan, double* Lg, int ln) {
     QPB_SMEM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -163,7 +187,7 @@ __device__ __noinline__ void pf_chol_update(int S, int nts, int kb0, int aug, in
     double* M = qsm + S;
     double* P = qsm + pan;
 #pragma unroll 1
-    for (int k = kb0; k < nts; ++k) {
+    for (int k = kb0; k < (kSetup ? kend : nts); ++k) {
         const int k0 = 8 * k;
         QPB_TICK1(40);
         named_bar_sync(1, kNT);                              // T_k is in the diagonal tile
@@ -182,6 +206,10 @@ __device__ __noinline__ void pf_chol_update(int S, int nts, int kb0, int aug, in
                 double d0 = 0.0, d1 = 0.0;
                 dmma884(d0, d1, a0, bT0);
                 dmma884(d0, d1, a1, bT1);
+                if (kSetup && Lg != nullptr && r < ln) {     // the plain factor, packed lower (columns k0 + 2q, + 1 < r)
+                    double* lrow = Lg + ((int64_t)r * (r + 1)) / 2 + k0 + 2 * q;
+                    lrow[0] = d0; lrow[1] = d1;
+                }
                 // rows of block k+1 belong to the chain warp in the shared scratch: keep a private copy past its end
                 double* pl = P + ((i == k + 1) ? (8 * nts + g) : r) * kPanLd;
                 *reinterpret_cast<double2*>(pl + 2 * q) = make_double2(d0, d1);
@@ -256,9 +284,18 @@ __device__ __noinline__ void pf_chol_update(int S, int nts, int kb0, int aug, in
     }
 }
 
+__device__ __forceinline__ void pf_chol_update(int S, int nts, int kb0, int aug, int pan) {
+    pf_chol_update_t<false>(S, nts, kb0, nts, aug, pan, nullptr, 0);
+}
+
 __device__ __forceinline__ void pf_chol(int S, int nts, int kb0, int aug, int pan) {
     if (threadIdx.x < 32) pf_chol_chain(S, nts, kb0, pan);
     else pf_chol_update(S, nts, kb0, aug, pan);
+}
+// pre_factor_kkt flavour: block columns [kb0, kend) only, optional emission of the plain factor (see pf_chol_chain_t)
+__device__ __forceinline__ void pf_chol_setup(int S, int nts, int kb0, int kend, int aug, int pan, double* Lg, int ln) {
+    if (threadIdx.x < 32) pf_chol_chain_t<true>(S, nts, kb0, kend, pan, Lg, ln);
+    else pf_chol_update_t<true>(S, nts, kb0, kend, aug, pan, Lg, ln);
 }
 
 // ---- substitutions (order n = 8 nts <= kNT: thread tid owns entry tid) ----------------------------------------------
