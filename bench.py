@@ -302,56 +302,75 @@ def run_b200(args, rank, world, local_rank):
         return z
 
     settle_steps = settle(step, args.warmup, NCOPIES)
-    # The step is 3 kernels behind ~0.4 ms of Python: capture forward+backward of every input copy in a CUDA graph
-    # (same kernels, same C-ABI calls: qpth_b200.qp.solve_forward / solve_backward are what QPFunction's
-    # forward/backward call) so that the timed loop is not at the mercy of host jitter. Falls back to eager.
+    # The step is 3 kernels behind ~0.5 ms of Python: capture QPFunction forward + autograd backward of every input
+    # copy in a CUDA graph so that the timed loop is not at the mercy of host jitter. Falls back to eager.
     launch_mode = "eager"
     last_iters = None
     serial_step = None
 
-    def capture_graphs():
+    def capture_graphs(user_level=True):
+        """One CUDA graph per input copy of the step. user_level: QPFunction forward + autograd backward (what the e2e leg
+        captures, minus the copies); else the two functions QPFunction.forward / .backward call (qpth_b200.qp.solve_forward
+        / solve_backward: same kernels, same C-ABI calls, no autograd bookkeeping)."""
         from qpth_b200.qp import solve_forward, solve_backward
         flags, want = [False] * 6, [True, True, True, True, False, False]
 
         def raw_step(t):
+            if user_level:
+                for v in t.values():
+                    v.grad = None
+                z = f(t["Q"], t["p"], t["G"], t["h"], e, e)
+                z.backward(dl)
+                return f.last_solve(), z
             st_ = solve_forward(t["Q"].detach(), t["p"].detach(), t["G"].detach(), t["h"].detach(), e, e,
                                 verbose=-1, check_Q_spd=False)
             return st_, solve_backward(st_, dl, flags, want)
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
+        # fresh leaves that only ever see the capture stream (the AccumulateGrad nodes of `batches` belong to the default
+        # stream the eager warm-up ran on, which invalidates a capture of backward on another stream)
+        leaves = [{k: v.detach().clone().requires_grad_(True) for k, v in t.items()} for t in batches] if user_level else batches
         with torch.cuda.stream(side):
-            for t in batches[:2]:
+            for t in leaves[:3]:
                 raw_step(t)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graphs, keep = [], []
-        for t in batches:
+        for t in leaves:
             gph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gph):
+            with torch.cuda.graph(gph, stream=side):
                 keep.append(raw_step(t))
             graphs.append(gph)
+        torch.cuda.synchronize()
+        keep.append(leaves)
         return graphs, keep
 
     if os.environ.get("QPB_BENCH_GRAPHS", "1") == "1":
-        try:
-            graphs, keep = capture_graphs()
+        for user_level in (True, False):
+            try:
+                graphs, keep = capture_graphs(user_level)
 
-            def step(i):                                          # noqa: F811
-                graphs[i % NCOPIES].replay()
-            last_iters = keep[-1][0].iters
-            launch_mode = "cuda_graph"
-            if bench_mode != "latency":                           # the single-stream leg: one QP per SM
-                qpmod.MODE = "latency"
-                lat_graphs, lat_keep = capture_graphs()
+                def step(i):                                      # noqa: F811
+                    graphs[i % NCOPIES].replay()
+                last_iters = keep[-2][0].iters
+                launch_mode = "cuda_graph (QPFunction forward + autograd backward)" if user_level else "cuda_graph (solve_forward + solve_backward)"
+                if bench_mode != "latency":                       # the single-stream leg: one QP per SM
+                    qpmod.MODE = "latency"
+                    lat_graphs, lat_keep = capture_graphs(user_level)
+                    qpmod.MODE = bench_mode
+
+                    def serial_step(i):                           # noqa: F811
+                        lat_graphs[i % NCOPIES].replay()
+                break
+            except Exception as exc:                              # noqa: BLE001
+                sys.stderr.write("bench: CUDA graph capture (%s) failed (%s)\n" % ("user level" if user_level else "solve_* level", str(exc)[:200]))
                 qpmod.MODE = bench_mode
-
-                def serial_step(i):                               # noqa: F811
-                    lat_graphs[i % NCOPIES].replay()
-        except Exception as exc:                                  # noqa: BLE001
-            sys.stderr.write("bench: CUDA graph capture failed (%s); using the eager loop\n" % str(exc)[:200])
-            qpmod.MODE = bench_mode
-            torch.cuda.synchronize()
+                launch_mode, serial_step = "eager", None
+                try:
+                    torch.cuda.synchronize()
+                except Exception:                                 # noqa: BLE001
+                    pass
     # `value`: K steps with the inputs resident in HBM. A step's kernels have 128 CTAs (one QP each); the GPU holds
     # 148 (one QP per SM), 296 or 444 (two / three QPs per SM) at a time and a QP leaves its slot as soon as it has converged
     # (12 Newton iterations on average, 16-18 for the slowest QP of a batch), so a single stream idles most of the
@@ -402,7 +421,7 @@ def run_b200(args, rank, world, local_rank):
         sampler.start()
     ms = timed_window(args.steps, done, use_streams)
     clocks = sampler.stop() if sampler else None
-    iters_mean = float((last_iters if launch_mode == "cuda_graph" else f.last_solve().iters).float().mean())
+    iters_mean = float((last_iters if launch_mode.startswith("cuda_graph") else f.last_solve().iters).float().mean())
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device=dev)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)

@@ -181,6 +181,17 @@ int qpb200_qp_host(int device, int nbatch, int nz, int nineq, int neq,
                    double* zhat_host, double* dQ_host, double* dp_host, double* dG_host,
                    double* dh_host, double* dA_host, double* db_host, int* spd_flag_host);
 
+/* The OptNet parameterisation either side of the path (example-cls-layer.ipynb:125-129): SHARED parameters L (nz x nz, its
+ * lower triangle is used), G (nineq x nz), z0, s0 define Q = tril(L) tril(L)^T + eps I and h = G z0 + s0; `construct`
+ * builds both in one launch, `chain` maps the (batch-mean) QP gradients dQ, dG_qp, dh back onto the parameters:
+ * dL = tril((dQ + dQ^T) tril(L)), dG = dG_qp + dh z0^T, dz0 = G^T dh, ds0 = dh. qpth_b200/layers.py wraps them with
+ * QPFunction's kernels in one autograd.Function. */
+int qpb200_optnet_construct(int nz, int nineq, const double* L, const double* G, const double* z0, const double* s0,
+                            double eps, double* Q, double* h, void* stream);
+int qpb200_optnet_chain(int nz, int nineq, const double* L, const double* G, const double* z0, const double* dQ,
+                        const double* dG_qp, const double* dh, double* dL, double* dG, double* dz0, double* ds0,
+                        void* stream);
+
 /* Transfer helper for SYMMETRIC (nbatch, n, n) matrices - Q on its way in, dQ on its way out (qp.py:157-158 builds dQ
  * as 1/2 (dx z^T + z dx^T)): only the lower triangle crosses PCIe, as `band`-row strips (strip b = rows [b band, (b+1)
  * band) x columns [0, (b+1) band)), one strided 3-D copy per strip on `stream`. The part of the destination above the

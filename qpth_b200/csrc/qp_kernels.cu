@@ -1027,6 +1027,55 @@ k_setup_pf(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __re
     for (int i = tid; i < pf_elems(nts); i += kThreads) Kg[i] = SQ[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// OptNet parameterisation either side of the path (example-cls-layer.ipynb:125-129):
+//   construct:  Q = tril(L) tril(L)^T + eps I,   h = G z0 + s0           (shared parameters: one system per batch)
+//   chain:      dL = tril((dQ + dQ^T) tril(L)),  dG = dG_qp + dh z0^T,  dz0 = G^T dh,  ds0 = dh
+// One launch each (n, m <= a few hundred: one thread per output element, rows of L / G read coalesced), instead of the
+// eight torch kernels and their (n x n) temporaries on either side of every QPFunction call.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_optnet_construct(int n, int m, const double* __restrict__ L, const double* __restrict__ G,
+                                   const double* __restrict__ z0, const double* __restrict__ s0, double eps,
+                                   double* __restrict__ Q, double* __restrict__ h) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n * n) {
+        const int r = idx / n, c = idx - r * n;
+        const int kmax = r < c ? r : c;
+        double acc = (r == c) ? eps : 0.0;
+        for (int k = 0; k <= kmax; ++k) acc = fma(L[r * n + k], L[c * n + k], acc);
+        Q[idx] = acc;
+    } else if (idx < n * n + m) {
+        const int i = idx - n * n;
+        double acc = s0[i];
+        for (int k = 0; k < n; ++k) acc = fma(G[i * n + k], z0[k], acc);
+        h[i] = acc;
+    }
+}
+__global__ void k_optnet_chain(int n, int m, const double* __restrict__ L, const double* __restrict__ G,
+                               const double* __restrict__ z0, const double* __restrict__ dQ,
+                               const double* __restrict__ dGq, const double* __restrict__ dh, double* __restrict__ dL,
+                               double* __restrict__ dG, double* __restrict__ dz0, double* __restrict__ ds0) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n * n) {
+        const int r = idx / n, c = idx - r * n;
+        double acc = 0.0;
+        if (c <= r)                                          // dL[r][c] = sum_{k >= c} (dQ[r][k] + dQ[k][r]) L[k][c]
+            for (int k = c; k < n; ++k) acc = fma(dQ[r * n + k] + dQ[k * n + r], L[k * n + c], acc);
+        dL[idx] = acc;
+    } else if (idx < n * n + m * n) {
+        const int j = idx - n * n, i = j / n, c = j - i * n;
+        dG[j] = dGq[j] + dh[i] * z0[c];
+    } else if (idx < n * n + m * n + n) {
+        const int c = idx - n * n - m * n;
+        double acc = 0.0;
+        for (int i = 0; i < m; ++i) acc = fma(G[i * n + c], dh[i], acc);
+        dz0[c] = acc;
+    } else if (idx < n * n + m * n + n + m) {
+        const int i = idx - n * n - m * n - n;
+        ds0[i] = dh[i];
+    }
+}
+
 // fp64 FMA issue-rate probe: 8 independent DFMA chains per thread (roofline denominator for bench.py)
 __global__ void k_dfma_probe(int iters, double* out) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
@@ -1680,6 +1729,25 @@ int qpb200_copy_lower(const double* src, double* dst, int nbatch, int n, int ban
         p.kind = direction ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
         CK(cudaMemcpy3DAsync(&p, st));
     }
+    return QPB200_OK;
+}
+
+int qpb200_optnet_construct(int nz, int nineq, const double* L, const double* G, const double* z0, const double* s0,
+                            double eps, double* Q, double* h, void* stream) {
+    if (nz <= 0 || nineq <= 0 || !L || !G || !z0 || !s0 || !Q || !h) return QPB200_ERR_BAD_ARG;
+    const int total = nz * nz + nineq, TB = 128;
+    k_optnet_construct<<<(total + TB - 1) / TB, TB, 0, (cudaStream_t)stream>>>(nz, nineq, L, G, z0, s0, eps, Q, h);
+    CK(cudaGetLastError());
+    return QPB200_OK;
+}
+
+int qpb200_optnet_chain(int nz, int nineq, const double* L, const double* G, const double* z0, const double* dQ,
+                        const double* dG_qp, const double* dh, double* dL, double* dG, double* dz0, double* ds0,
+                        void* stream) {
+    if (nz <= 0 || nineq <= 0 || !L || !G || !z0 || !dQ || !dG_qp || !dh || !dL || !dG || !dz0 || !ds0) return QPB200_ERR_BAD_ARG;
+    const int total = nz * nz + nineq * nz + nz + nineq, TB = 128;
+    k_optnet_chain<<<(total + TB - 1) / TB, TB, 0, (cudaStream_t)stream>>>(nz, nineq, L, G, z0, dQ, dG_qp, dh, dL, dG, dz0, ds0);
+    CK(cudaGetLastError());
     return QPB200_OK;
 }
 

@@ -61,6 +61,8 @@ struct FCtx {
     uint32_t lphase;      // parity of the next completion on bar[0] (W/L staging)
     uint32_t kbytes;      // size of the K template (square or staircase layout)
     bool kpending;
+    bool lglobal;         // W/L-from-global product-form kernels: chol(Q) does not fit the (dead) S region it would visit,
+                          // so the two packed-L substitutions read it from global memory
 };
 #define FV(i) (C.L.vec + (i) * C.L.vl)
 
@@ -123,7 +125,8 @@ __device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double*
     }
     if (!kPF) build_tile_table(reinterpret_cast<uint16_t*>(qsm + C.L.tab), (D.msp - D.ep) >> 3, tid);
     __syncthreads();
-    if (kCoop && kPF) {
+    C.lglobal = kCoop && kPF && (D.lp > s_doubles(D, true));
+    if (kCoop && kPF && C.lglobal) {
         f_issue_K(D, C);                                         // nothing is staged: L is read from global memory
         _Pragma("unroll 1") for (int i = tid; i < D.n; i += kNT) qsm[FV(F_DINVL) + i] = 1.0 / C.Lg[(i * (i + 1)) / 2 + i];
         return C;
@@ -145,17 +148,17 @@ __device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double*
     return C;
 }
 
-// x~ = L^-1 x and x = L^-T x~ with the packed L in shared memory, or (global W/L + product form) straight from global
-template <bool kGlobalL>
+// x~ = L^-1 x and x = L^-T x~ with the packed L in shared memory (staged into the dead S region in the W/L-from-global
+// kernels: 13 block steps with a global load on each step's critical path were 6.7 % of the warp samples of the
+// co-resident capture, profiles/r2l_*), or straight from global memory when it does not fit there
 __device__ __forceinline__ void f_whiten_x(const KDims& D, const FCtx& C, int b, int u) {
     QPB_SMEM;
-    if (kGlobalL) trsv_fwd(C.Lg, PackedIdx{}, D.n, 0, D.n, qsm + FV(F_DINVL), qsm + b, qsm + u, (int)threadIdx.x, kNT);
+    if (C.lglobal) trsv_fwd(C.Lg, PackedIdx{}, D.n, 0, D.n, qsm + FV(F_DINVL), qsm + b, qsm + u, (int)threadIdx.x, kNT);
     else f_whiten(C.L.Lp, D.n, FV(F_DINVL), b, u);
 }
-template <bool kGlobalL>
 __device__ __forceinline__ void f_unwhiten_x(const KDims& D, const FCtx& C, int u, int w) {
     QPB_SMEM;
-    if (kGlobalL) trsv_bwd(C.Lg, PackedIdx{}, D.n, qsm + FV(F_DINVL), qsm + u, qsm + w, (int)threadIdx.x, kNT);
+    if (C.lglobal) trsv_bwd(C.Lg, PackedIdx{}, D.n, qsm + FV(F_DINVL), qsm + u, qsm + w, (int)threadIdx.x, kNT);
     else f_unwhiten(C.L.Lp, D.n, FV(F_DINVL), u, w);
 }
 
@@ -261,7 +264,6 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     __syncthreads();
 #endif
     FCtx C = f_make_ctx<kCoop, kPF>(D, qp, Lfac, Wfac, Kfac, sF);
-    constexpr bool kGL = kCoop && kPF;                          // packed L read from global memory, nothing staged
     QPB_TICK(0);
     const int pt = FV(F_PT), xt = FV(F_XT), rxt = FV(F_RXT), s = FV(F_S), v = FV(F_V), rv = FV(F_RV),
               hW = FV(F_HW), w = FV(F_W), dsa = FV(F_DSA), ds = FV(F_DS), d = FV(F_D), hb = FV(F_HB),
@@ -284,8 +286,8 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     }
     __syncthreads();
     QPB_TICK(1);
-    f_whiten_x<kGL>(D, C, t1, pt);                              // p~ = L^-1 p
-    if (kCoop && !kPF) {                                        // L leaves the S workspace: the first K copy may land
+    f_whiten_x(D, C, t1, pt);                              // p~ = L^-1 p
+    if (kCoop && !C.lglobal) {                                  // L leaves the S workspace: the first K copy may land
         __syncthreads();
         f_issue_K(D, C);
     }
@@ -460,12 +462,12 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     // ---- outputs: x = L^-T x~_best, y, z, s of the returned iterate (batch.py:205-207)
     __syncthreads();
     QPB_TICK(16);
-    if (kCoop && !kPF) {                                         // the S workspace is dead: L comes back for x = L^-T x~
+    if (kCoop && !C.lglobal) {                                   // the S workspace is dead: L comes back for x = L^-T x~
         if (C.kpending) f_wait_K(C);
         __syncthreads();
         f_stage_L(D, C);
     }
-    f_unwhiten_x<kGL>(D, C, FV(F_BXT), t0);
+    f_unwhiten_x(D, C, FV(F_BXT), t0);
     if (C.kpending) f_wait_K(C);                                 // drain the in-flight copy before exit
     _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) zhat[(int64_t)qp * n + i] = qsm[t0 + i];
     _Pragma("unroll 1") for (int i = tid; i < m; i += kNT) {
@@ -501,7 +503,6 @@ k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ 
     const int qp = blockIdx.x;
     const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
     FCtx C = f_make_ctx<kCoop, kPF>(D, qp, Lfac, Wfac, Kfac, sF);
-    constexpr bool kGL = kCoop && kPF;
     const int t = FV(F_PT), d = FV(F_D), hW = FV(F_HW), aug = FV(F_AUG), w = FV(F_W), t0 = FV(F_T0),
               t1 = FV(F_T1), rsv = FV(F_S), c2 = FV(F_RV), dxt = FV(F_RXT), dxo = FV(F_XT);
     _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[t1 + i] = rx_in[(int64_t)qp * n + i];
@@ -528,8 +529,8 @@ k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ 
         qsm[aug + i] = 0.0;
     }
     __syncthreads();
-    f_whiten_x<kGL>(D, C, t1, t);                               // t = L^-1 rx
-    if (kCoop && !kPF) {
+    f_whiten_x(D, C, t1, t);                               // t = L^-1 rx
+    if (kCoop && !C.lglobal) {
         __syncthreads();
         f_issue_K(D, C);
     }
@@ -539,8 +540,8 @@ k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ 
     __syncthreads();
     if (kPF) f_factor_and_solve_pf(D, C); else f_factor_and_solve(D, C, false);   // w = [dy; dz]
     mv_cols<kCoop>(D, C, w, t0, t1, dxt, t, -1.0, -1, -1.0);
-    if (kCoop && !kPF) f_stage_L(D, C);                         // (mv_cols ended with a block barrier; no K copy in flight)
-    f_unwhiten_x<kGL>(D, C, dxt, dxo);                          // dx = L^-T dx~
+    if (kCoop && !C.lglobal) f_stage_L(D, C);                   // (mv_cols ended with a block barrier; no K copy in flight)
+    f_unwhiten_x(D, C, dxt, dxo);                          // dx = L^-T dx~
     _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) dx_out[(int64_t)qp * n + i] = qsm[dxo + i];
     _Pragma("unroll 1") for (int i = tid; i < m; i += kNT) {
         dz_out[(int64_t)qp * m + i] = qsm[w + ep + i];

@@ -41,7 +41,8 @@ def test_plan_shapes(lib):
     assert (p.neq_pad, p.ms) == (16, 66)
     p = _lib.plan_for(200, 200, 0)         # product-form "large problem" kernels: factor in shared memory, W / L from L2
     assert p.smem_resident == 0 and (p.pf, p.pf_global, p.pf2_ok) == (1, 1, 0) and p.pf_smem_bytes <= 232448 - 1024
-    assert p.solve_scratch_elems == 0 and p.setup_scratch_elems > 0 and p.K_elems == 32 * 25 * 25 + 64 * 25
+    assert p.solve_scratch_elems == 0 and p.setup_pf == 1 and p.setup_scratch_elems == 0 and p.K_elems == 32 * 25 * 25 + 64 * 25
+    assert p.setup_pf_smem_bytes <= 232448 - 1024 and _lib.plan_for(100, 100, 0).setup_pf == 0      # (k_setup_fast is faster there)
     p = _lib.plan_for(200, 200, 16)        # does not fit any shared-memory variant: global-scratch kernels
     assert p.pf == 0 and p.solve_scratch_elems > 0
     p = _lib.plan_for(100, 100, 0)         # both product-form variants; the second one fits twice into an SM
