@@ -94,6 +94,17 @@ def sweep_problem(i):
     return dict(Q=Q, p=p, G=G, h=h, A=A, b=b, dl=dl)
 
 
+def sudoku_structured_problem(seed=31, B=12, n=64, e=40):
+    """The structure of example-sudoku.ipynb:305-323 (the OptNet sudoku layer for 4 x 4 boards): Q = 0.1 I (diagonal),
+    G = -I, h = 0 (z >= 0), a SHARED dense A with b = A z0 for a strictly positive z0, batched p. This is the problem
+    class the reference's sparse path (SpQPFunction, dead code) was written for; here it goes through the dense kernels
+    (order of the reduced system: 40 + 64 = 104)."""
+    rs = np.random.RandomState(seed)
+    A = rs.randn(e, n)
+    z0 = rs.rand(n) + 0.1
+    return dict(Q=0.1 * np.eye(n), p=-rs.rand(B, n), G=-np.eye(n), h=np.zeros(n), A=A, b=A @ z0, dl=rs.randn(B, n))
+
+
 def _testpy(tag_kw):
     def build():
         return testpy_problem(**tag_kw)
@@ -121,6 +132,7 @@ CASES = {
     "band_smem_eq": (lambda: random_qp_batch(6, 24, 116, 4, seed=22), True),
     "band_setup": (lambda: random_qp_batch(6, 150, 20, 0, seed=23), False),      # fast=1, setup_fast=0
     "band_setup_eq": (lambda: random_qp_batch(6, 140, 24, 3, seed=24), False),
+    "sudoku_structured": (sudoku_structured_problem, True),                     # diagonal Q, G = -I, shared A
 }
 for _i in range(N_SWEEP):
     CASES["sweep%02d" % _i] = ((lambda i=_i: sweep_problem(i)), True)

@@ -54,12 +54,14 @@ EXPECTED_PATH = {
     "band_smem": (0, 0, 1), "band_smem_eq": (0, 0, 1),           # nineq > 104: generic shared-memory kernels
     "band_setup": (1, 0, 1), "band_setup_eq": (1, 0, 1),         # nz > 104: fast solve kernels, generic setup
     "c4": (0, 0, 0),                                             # 200 x 200: global-scratch kernels
+    "sudoku_structured": (1, 1, 1),                              # diagonal Q, G = -I, shared A (order 40 + 64 = 104)
 }
 
 
 # product-form kernels (qp_pf.cuh) are the default wherever they fit: (pf, pf_global)
 EXPECTED_PF = {"c2": (1, 0), "c3": (1, 0), "c5_shard0": (1, 0), "c3_b64": (1, 0), "c4_small": (1, 0),
-               "band_smem": (1, 0), "band_smem_eq": (1, 0), "band_setup": (1, 0), "band_setup_eq": (1, 0), "c4": (1, 1)}
+               "band_smem": (1, 0), "band_smem_eq": (1, 0), "band_setup": (1, 0), "band_setup_eq": (1, 0), "c4": (1, 1),
+               "sudoku_structured": (1, 0)}
 # cases re-run with QPB200_PF=1 (product-form kernels wherever they fit): every non-tiny kernel family
 PF_CASES = ["c2", "c3_b64", "c4_small", "c5_shard0", "band_setup", "band_setup_eq", "band_smem_eq", "c4"]
 
