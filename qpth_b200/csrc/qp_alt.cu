@@ -80,6 +80,30 @@ int QPB_ALT_NAME(_forward)(const qpb200_plan* plan, size_t smem, int nbatch, con
     return alt_check_launch();
 }
 
+// the same with W and chol(Q) staged in shared memory (one QP per SM, latency mode) - only built at 512 threads
+int QPB_ALT_NAME(_forward_res)(const qpb200_plan* plan, size_t smem, int nbatch, const double* p, int64_t sp, const double* h,
+                               int64_t sh, const double* b, int64_t sb, const double* Lfac, const double* Wfac,
+                               const double* Kfac, int sF, double eps, double stall_tol, double best_tie, int notImprovedLim,
+                               int maxIter, double* zhat, double* lam, double* slacks, double* nus, int* iters,
+                               double* best_resid, double* trace, void* stream) {
+#if QPB_NT == 512
+    cudaStream_t st = (cudaStream_t)stream;
+    const KDims D = alt_dims(plan);
+    static size_t cur[16];
+    int rc = alt_set_smem(k_forward_fast<false, true, 0>, smem, cur);
+    if (rc) return rc;
+    k_forward_fast<false, true, 0><<<nbatch, qpb::fast::kNT, smem, st>>>(
+        D, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF, eps, stall_tol, best_tie, notImprovedLim, maxIter, zhat, lam,
+        slacks, nus, iters, best_resid, trace);
+    return alt_check_launch();
+#else
+    (void)plan; (void)smem; (void)nbatch; (void)p; (void)sp; (void)h; (void)sh; (void)b; (void)sb; (void)Lfac; (void)Wfac;
+    (void)Kfac; (void)sF; (void)eps; (void)stall_tol; (void)best_tie; (void)notImprovedLim; (void)maxIter; (void)zhat;
+    (void)lam; (void)slacks; (void)nus; (void)iters; (void)best_resid; (void)trace; (void)stream;
+    return QPB200_ERR_BAD_ARG;
+#endif
+}
+
 int QPB_ALT_NAME(_solve_kkt)(const qpb200_plan* plan, size_t smem, int nbatch, const double* d, const double* rx,
                              const double* rs, const double* rz, const double* ry, const double* Lfac, const double* Wfac,
                              const double* Kfac, int sF, double* dx, double* ds, double* dz, double* dy, void* stream) {

@@ -1156,6 +1156,9 @@ extern "C" {
                                   double*, double*, void*);
 QPB_ALT_DECL(192)
 QPB_ALT_DECL(512)
+int qpb200_alt512_forward_res(const qpb200_plan*, size_t, int, const double*, int64_t, const double*, int64_t,
+                              const double*, int64_t, const double*, const double*, const double*, int, double, double,
+                              double, int, int, double*, double*, double*, double*, int*, double*, double*, void*);
 #undef QPB_ALT_DECL
 void qpb200_internal_cuda_error(int err, const char* what) { cuda_fail((cudaError_t)err, what); }
 }
@@ -1273,6 +1276,8 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
             // large orders (nz = nineq = 200): 15 update warps instead of 7 (the factorization is update-bound there)
             const char* e512 = getenv("QPB200_NT512");
             plan->pf_threads = (plan->pf_global && msp > 128 && !(e512 != nullptr && e512[0] == '0')) ? 512 : 256;
+            // experiment knob: "2" = also the RESIDENT forward kernel at 512 threads (backward / solve_kkt stay at 256)
+            if (!plan->pf_global && e512 != nullptr && e512[0] == '2') plan->pf_threads = 512;
             plan->K_elems = (int64_t)qpb::pf::pf_elems(msp >> 3);
             plan->solve_scratch_elems = 0;                   // the factor lives in shared memory: no per-QP global workspace
             // pre_factor_kkt on the same machinery (k_setup_pf) whenever its shared memory fits
@@ -1388,6 +1393,10 @@ int qpb200_forward(const qpb200_plan* plan, int nbatch, const double* p, int64_t
                                          stall_tol, best_tie, notImprovedLim, maxIter, zhat, lam, slacks, nus, iters, best_resid,
                                          trace, stream);
         else if (plan->pf_global) QPB_LAUNCH_PF(true, 0);
+        else if (plan->pf_threads == 512)                    // resident (latency) kernel at 512 threads: 15 update warps
+            return qpb200_alt512_forward_res(plan, (size_t)plan->pf_smem_bytes, nbatch, p, sp, h, sh, b, sb, Lfac, Wfac, Kfac, sF,
+                                             eps, stall_tol, best_tie, notImprovedLim, maxIter, zhat, lam, slacks, nus, iters,
+                                             best_resid, trace, stream);
         else QPB_LAUNCH_PF(false, 0);
 #undef QPB_LAUNCH_PF
     } else if (plan->fast && plan->coop && plan->coop_ok) {

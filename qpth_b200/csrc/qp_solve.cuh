@@ -103,7 +103,11 @@ __device__ __forceinline__ void f_stage_L(const KDims& D, FCtx& C) {
 // Stage W and packed L with TMA, start the first K copy, build the tile table.
 // kCoop: only L is staged (into the S workspace, for the whitening of the caller's first vector); the caller issues
 // the first K copy itself once it is done with L (f_issue_K after a block barrier).
-template <bool kCoop, bool kPF = false>
+// kStageL (W/L-from-global product-form kernels): stage chol(Q) in the dead S region for the two packed-L substitutions
+// instead of reading it from global memory inside them. Measured (r2o/r2z, B = 8192): the backward kernel, whose one
+// iteration makes the substitutions a large share, gains 24 %; the forward kernel LOSES 2 % (the first K copy can no
+// longer overlap the whitening) - so only the backward / solve_kkt kernel stages.
+template <bool kCoop, bool kPF = false, bool kStageL = false>
 __device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double* Lfac, const double* Wfac,
                                            const double* Kfac, int sF) {
     QPB_SMEM;
@@ -125,7 +129,7 @@ __device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double*
     }
     if (!kPF) build_tile_table(reinterpret_cast<uint16_t*>(qsm + C.L.tab), (D.msp - D.ep) >> 3, tid);
     __syncthreads();
-    C.lglobal = kCoop && kPF && (D.lp > s_doubles(D, true));
+    C.lglobal = kCoop && kPF && (!kStageL || D.lp > s_doubles(D, true));
     if (kCoop && kPF && C.lglobal) {
         f_issue_K(D, C);                                         // nothing is staged: L is read from global memory
         _Pragma("unroll 1") for (int i = tid; i < D.n; i += kNT) qsm[FV(F_DINVL) + i] = 1.0 / C.Lg[(i * (i + 1)) / 2 + i];
@@ -502,7 +506,7 @@ k_kkt_fast(KDims D, const double* __restrict__ d_in, const double* __restrict__ 
     const int tid = threadIdx.x;
     const int qp = blockIdx.x;
     const int n = D.n, m = D.m, e = D.e, ep = D.ep, ms = D.ms, msp = D.msp;
-    FCtx C = f_make_ctx<kCoop, kPF>(D, qp, Lfac, Wfac, Kfac, sF);
+    FCtx C = f_make_ctx<kCoop, kPF, true>(D, qp, Lfac, Wfac, Kfac, sF);
     const int t = FV(F_PT), d = FV(F_D), hW = FV(F_HW), aug = FV(F_AUG), w = FV(F_W), t0 = FV(F_T0),
               t1 = FV(F_T1), rsv = FV(F_S), c2 = FV(F_RV), dxt = FV(F_RXT), dxo = FV(F_XT);
     _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[t1 + i] = rx_in[(int64_t)qp * n + i];
