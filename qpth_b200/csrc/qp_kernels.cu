@@ -881,7 +881,7 @@ k_setup_fast(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __
 // setup kernel works from global scratch on one CTA: 1.03 ms -> see profiles/r2n_*).
 // ---------------------------------------------------------------------------------------------
 namespace fk {
-constexpr int kSetupStage = 4;          // row tiles of [A; G] staged at a time (one warp each); fewer if shared memory is short
+constexpr int kSetupStage = 6;          // row tiles of [A; G] staged at a time (one warp each); fewer if shared memory is short
 struct PLayout { int SQ, pan, aug, stage, ldt, nts, nstage, total; };
 __host__ __device__ inline PLayout setup_pf_layout(const KDims& D) {
     PLayout L;
@@ -922,6 +922,10 @@ k_setup_pf(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __re
     double* SQ = qsm + PL.SQ;
     __shared__ int s_flag;
     if (tid == 0) s_flag = 0;
+#ifdef QPB_TIMING
+    if (threadIdx.x == 0) { for (int i = 0; i < 128; ++i) s_tim[i] = 0; s_tim[128] = clock64(); s_tim2 = s_tim[128]; }
+    __syncthreads();
+#endif
     // ---- 1. Q (lower triangle, identity padded, + eps I in the regularised variant) -> staircase
     for (int r = warp; r < np; r += kThreads / 32) {
         const int off = pf_rowoff(r), len = 8 * (r >> 3) + 8;
@@ -933,7 +937,9 @@ k_setup_pf(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __re
     }
     for (int i = tid; i < (PL.nts << 3); i += kThreads) qsm[PL.aug + i] = 0.0;
     __syncthreads();
+    QPB_TICK(34);   // staging
     pf_chol_setup(PL.SQ, ntq, 0, ntq, PL.aug, PL.pan, Lg, n);
+    QPB_TICK(35);   // chol(Q)
     // SPD check (qp.py:81-85): every reciprocal pivot (diagonal of the T_k) must be a positive finite number
     for (int i = tid; i < n; i += kThreads) {
         const double ri = SQ[pf_rowoff(i) + i];
@@ -991,6 +997,7 @@ k_setup_pf(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __re
         }
     }
     __syncthreads();                                         // W is in global memory (visible to the block), chol(Q) is dead
+    QPB_TICK(37);   // W
     if (tid == 0) spd_flag[sys] = s_flag;
     // ---- 3. K = W W^T -> staircase (lower tiles), unit diagonal on dummy / pad rows, + eps on the real equality rows
     {
@@ -1005,11 +1012,25 @@ k_setup_pf(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __re
             const double* pb = Wg + (int64_t)(rb < ms ? rb : 0) * D.ldw + q;
             const bool oka = ra < ms, okb = rb < ms;
             double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;   // two accumulator chains
-            for (int kk = 0; kk < np; kk += 8) {             // (W has ldw >= n + padding zeros up to the next multiple of 4... guard by n)
-                const double x0 = (oka && kk + q < n) ? pa[kk] : 0.0, y0 = (okb && kk + q < n) ? pb[kk] : 0.0;
-                const double x1 = (oka && kk + 4 + q < n) ? pa[kk + 4] : 0.0, y1 = (okb && kk + 4 + q < n) ? pb[kk + 4] : 0.0;
-                dmma884(c0, c1, x0, y0);
-                dmma884(e0, e1, x1, y1);
+            // W comes back from L2 (written by this CTA in step 2): 28 loads in flight per lane, then their 14 DMMAs
+#pragma unroll 1
+            for (int kk0 = 0; kk0 < np; kk0 += 56) {
+                double x0[7], y0[7], x1[7], y1[7];
+#pragma unroll
+                for (int u = 0; u < 7; ++u) {
+                    const int kk = kk0 + 8 * u;
+                    x0[u] = (oka && kk + q < n) ? pa[kk] : 0.0;
+                    y0[u] = (okb && kk + q < n) ? pb[kk] : 0.0;
+                    x1[u] = (oka && kk + 4 + q < n) ? pa[kk + 4] : 0.0;
+                    y1[u] = (okb && kk + 4 + q < n) ? pb[kk + 4] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 7; ++u) {
+                    if (kk0 + 8 * u < np) {                  // (warp-uniform)
+                        dmma884(c0, c1, x0[u], y0[u]);
+                        dmma884(e0, e1, x1[u], y1[u]);
+                    }
+                }
             }
             const int rr = 8 * ti + g, cc = 8 * tj + 2 * q;
             double v0 = c0 + e0, v1 = c1 + e1;
@@ -1021,10 +1042,16 @@ k_setup_pf(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __re
         }
     }
     __syncthreads();
+    QPB_TICK(39);   // K = W W^T
     // ---- 4. equality block in product form (columns [0, ep)), then K -> global
     if (ep > 0) pf_chol_setup(PL.SQ, nts, 0, ep >> 3, PL.aug, PL.pan, nullptr, 0);
     __syncthreads();
+    QPB_TICK(45);   // equality block
     for (int i = tid; i < pf_elems(nts); i += kThreads) Kg[i] = SQ[i];
+    QPB_TICK(46);   // write K
+#ifdef QPB_TIMING
+    if (tid == 0 && sys == 0) for (int i = 0; i < 128; ++i) g_tim[i] = s_tim[i];
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1282,11 +1309,13 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
             plan->solve_scratch_elems = 0;                   // the factor lives in shared memory: no per-QP global workspace
             // pre_factor_kkt on the same machinery (k_setup_pf) whenever its shared memory fits
             const int64_t spf = (int64_t)fk::setup_pf_layout(D).total * 8;
-            // measured (profiles/r2n_setup_pf.txt): 1.7x faster than the global-scratch setup at nz = nineq = 200 (1037 -> 598
-            // us), but SLOWER than k_setup_fast where that exists (C2, B = 8192: 3.65 vs 3.21 ms even at two per SM: the
-            // W sweep runs on 4 warps and K re-reads W from L2) - so it is the default only where there is no fast setup
+            // measured (profiles/r2n_setup_pf.txt, r2r_setup_pf_v2.txt): 1.7x faster than the global-scratch setup at nz =
+            // nineq = 200 (1037 -> 598 us), but still SLOWER than k_setup_fast at C2 (B = 8192: 3.38 vs 3.21 ms even at two
+            // per SM; phase table: W sweep 69k, K from L2 33k, chol(Q) + factor emission 45k cycles) - so it is the
+            // default only where there is no fast setup or the problem is small
             const char* esp = getenv("QPB200_SETUP_PF");     // development / A-B knob: "0" never, "1" wherever it fits
-            const bool want_spf = (esp != nullptr) ? (esp[0] == '1') : !setup_fast_ok;
+            // (nz <= 64: the 6-warp W sweep covers the whole of [A; G] in one or two rounds and it wins: C3 259 -> 199 us)
+            const bool want_spf = (esp != nullptr) ? (esp[0] == '1') : (!setup_fast_ok || nz <= 64);
             plan->setup_pf = (spf <= kMaxSmem && want_spf) ? 1 : 0;
             plan->setup_pf_smem_bytes = spf;
             if (plan->setup_pf) plan->setup_scratch_elems = 0;

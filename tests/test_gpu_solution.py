@@ -68,3 +68,26 @@ def test_solution_shape_errors():
     ok = torch.zeros(3, 4, dtype=torch.float64, device=DEV)
     with pytest.raises(RuntimeError):
         QPSolutionFunction()(t["Q"], t["p"], t["G"], t["h"], t["A"], t["b"], bad, ok, ok, torch.Tensor())
+
+
+def test_lower_triangle_strip_copies():
+    """qpb200_copy_lower (util.copy_lower_): the lower triangle of a batch of symmetric matrices crosses in strips, in both
+    directions; what lies above the strips in the destination is untouched."""
+    import torch
+    from qpth_b200.util import copy_lower_
+    B, n = 5, 37
+    h = torch.randn(B, n, n, dtype=torch.float64)
+    h = (h + h.transpose(1, 2)).contiguous().pin_memory()
+    for band in (8, 10, 37, 64):
+        d = torch.full((B, n, n), -7.0, dtype=torch.float64, device="cuda:0")
+        copy_lower_(d, h, band=band)
+        torch.cuda.synchronize()
+        dc = d.cpu()
+        assert torch.equal(torch.tril(dc), torch.tril(h))
+        r = torch.arange(n)
+        beyond = (r[None, :] >= ((r[:, None] // band) + 1) * band)          # columns past the strip of each row
+        assert bool((dc[:, beyond] == -7.0).all())
+        back = torch.zeros(B, n, n, dtype=torch.float64).pin_memory()
+        copy_lower_(back, d, band=band)
+        torch.cuda.synchronize()
+        assert torch.equal(torch.tril(back), torch.tril(h))
