@@ -431,8 +431,8 @@ def run_b200(args, rank, world, local_rank):
     # ---- e2e: host buffers, asynchronous options (check_Q_spd=False, verbose=-1) ...
     if os.environ.get("QPB_BENCH_E2E", "1") != "1":               # (development sweeps of the resident number only)
         if rank == 0:
-            print(json.dumps({"value": world * B * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps, "e2e": {"value": 0.0},
-                              "detail": {"serial_ms_per_step": serial_ms / args.steps, "steps_in_flight": inflight, "mean_newton_iters": iters_mean}}), flush=True)
+            return {"value": world * B * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps, "e2e": {"value": 0.0},
+                    "detail": {"serial_ms_per_step": serial_ms / args.steps, "steps_in_flight": inflight, "mean_newton_iters": iters_mean}}
         return None
     e2e_ms, windows, ksteps, NS, h2d, d2h, e2e_how = e2e_leg(f, dev, rank, world, args.steps, args.warmup, dl)
     # ... and with the reference's DEFAULT options (check_Q_spd=True, verbose=0): every forward then reads the
