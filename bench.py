@@ -14,6 +14,10 @@ Rank 0 prints ONE JSON line (contract in the task statement / DESIGN.md section 
 UNMODIFIED qpth package from oracle/_ref/ (put there by oracle/make_ref.sh; `cpu_baseline.kind` = "reference"),
 or, when that directory is absent, the oracle port oracle/pdipm_torch.py (`kind` = "port").
 
+The pipelined legs (`value`, `e2e`) replay CUDA graphs of the user-level step (QPFunction forward + autograd backward, plus
+the H2D / D2H copies for `e2e`) on 6 streams in the library's throughput mode (three QPs per SM); `detail.serial_*` is
+one stream in latency mode (one QP per SM).
+
 Extra measurements on the b200 line (rank 0): `detail.c4` (BASELINE config 4, cls-layer pattern), `detail.c5`
 (config 5: B=8192 scattered from rank 0 over the ranks through NCCL, z* gathered; N > 1 only),
 `reference_cuda` (the unmodified reference on CUDA tensors on the same GPU, N = 1 only).
@@ -544,7 +548,10 @@ def run_b200(args, rank, world, local_rank):
                    "settle_steps": settle_steps, "numa": numa, "mode": bench_mode,
                    "solve_kernels": ("product form" if plan.pf else "round-1") + (", three QPs per SM (192-thread CTAs; W, chol(Q) from L2)" if (plan.pf and plan.pf_three) else ", two QPs per SM (W, chol(Q) from L2)" if (plan.pf and plan.pf_two) else ", one QP per SM"),
                    "serial_kernels": "one QP per SM (latency mode)" if serial_step is not None else "same as value",
-                   "kernel_ms_alone": {"setup": setup_ms, "forward": k_ms, "backward": bwd_ms}},
+                   "kernel_ms_alone": {"setup": setup_ms, "forward": k_ms, "backward": bwd_ms},
+                   "parity": "fp64; GPU suite (tests/, -m gpu) vs outputs of the real reference: per-QP relative l2 of z*, nu <= 1e-8; "
+                             "lambda, slacks rtol 1e-6 / atol 1e-8 max|ref|; every gradient <= 1e-6 with the denominator floored at "
+                             "1e-4 of the batch maximum (tests/parity.py); measured worst case at C2: z 1.5e-11, gradients 1.5e-11"},
     }
     if world == 1 and os.environ.get("QPB_BENCH_C4", "1") == "1":
         try:
