@@ -882,7 +882,7 @@ k_setup_fast(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __
 // ---------------------------------------------------------------------------------------------
 namespace fk {
 constexpr int kSetupStage = 6;          // row tiles of [A; G] staged at a time (one warp each); fewer if shared memory is short
-struct PLayout { int SQ, pan, aug, stage, ldt, nts, nstage, total; };
+struct PLayout { int SQ, pan, aug, tab, stage, ldt, nts, nstage, total; };
 __host__ __device__ inline PLayout setup_pf_layout(const KDims& D) {
     PLayout L;
     const int np = (D.n + 7) & ~7;
@@ -891,7 +891,8 @@ __host__ __device__ inline PLayout setup_pf_layout(const KDims& D) {
     L.SQ = 0;
     L.pan = qpb::pf::pf_elems(L.nts) - 8 * qpb::pf::kPanLd;   // (its first 8 rows are never touched: overlap the staircase)
     L.aug = L.pan + (ord + 8) * qpb::pf::kPanLd;
-    L.stage = L.aug + ord;
+    L.tab = L.aug + ord;
+    L.stage = L.tab + ((qpb::pf::pf_tab_doubles(L.nts) + 1) & ~1);
     L.ldt = np + 4;
     const int room = (kMaxSmem / 8 - L.stage) / (8 * L.ldt);
     L.nstage = room < 1 ? 1 : (room > kSetupStage ? kSetupStage : room);
@@ -936,9 +937,10 @@ k_setup_pf(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __re
         }
     }
     for (int i = tid; i < (PL.nts << 3); i += kThreads) qsm[PL.aug + i] = 0.0;
+    pf_build_tab(PL.tab, PL.nts);
     __syncthreads();
     QPB_TICK(34);   // staging
-    pf_chol_setup(PL.SQ, ntq, 0, ntq, PL.aug, PL.pan, Lg, n);
+    pf_chol_setup(PL.SQ, ntq, 0, ntq, PL.aug, PL.pan, PL.tab, Lg, n);
     QPB_TICK(35);   // chol(Q)
     // SPD check (qp.py:81-85): every reciprocal pivot (diagonal of the T_k) must be a positive finite number
     for (int i = tid; i < n; i += kThreads) {
@@ -1044,7 +1046,7 @@ k_setup_pf(KDims D, const double* __restrict__ Q, int64_t sQ, const double* __re
     __syncthreads();
     QPB_TICK(39);   // K = W W^T
     // ---- 4. equality block in product form (columns [0, ep)), then K -> global
-    if (ep > 0) pf_chol_setup(PL.SQ, nts, 0, ep >> 3, PL.aug, PL.pan, nullptr, 0);
+    if (ep > 0) pf_chol_setup(PL.SQ, nts, 0, ep >> 3, PL.aug, PL.pan, PL.tab, nullptr, 0);
     __syncthreads();
     QPB_TICK(45);   // equality block
     for (int i = tid; i < pf_elems(nts); i += kThreads) Kg[i] = SQ[i];

@@ -35,7 +35,37 @@ constexpr int kPanLd = 12;              // row stride of the panel scratch (8 us
 
 // In-register factorization of an 8x8 SPD block (lower triangle in Lk, every lane holds all of it): on exit strictly
 // lower = L, diagonal = 1 / L_cc. A non-positive pivot gives NaN/inf everywhere below it.
+#ifndef QPB_PF_PAIRS
+#define QPB_PF_PAIRS 0     // 1: eliminate the columns of the 8x8 block in pairs (two rsqrt side by side); A/B knob
+#endif
 __device__ __forceinline__ void pf_factor8(double (&Lk)[36]) {
+#if QPB_PF_PAIRS
+    // with a = A_cc, b = A_c+1,c, e = A_c+1,c+1: second pivot = det / a, det = a e - b^2, so 1/L_c+1,c+1 = rsqrt(det) sqrt(a)
+    // and the two rsqrt (the longest link of the chain) run side by side
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+        const double a = Lk[QPB_LIDX(c, c)], b = Lk[QPB_LIDX(c + 1, c)], e = Lk[QPB_LIDX(c + 1, c + 1)];
+        const double r1 = f_rsqrt(a);
+        const double det = fma(a, e, -(b * b));
+        const double r2 = f_rsqrt(det) * (a * r1);
+        const double l10 = b * r1;
+        Lk[QPB_LIDX(c, c)] = r1;
+        Lk[QPB_LIDX(c + 1, c)] = l10;
+        Lk[QPB_LIDX(c + 1, c + 1)] = r2;
+#pragma unroll
+        for (int r = c + 2; r < 8; ++r) {
+            const double l1 = Lk[QPB_LIDX(r, c)] * r1;
+            Lk[QPB_LIDX(r, c)] = l1;
+            Lk[QPB_LIDX(r, c + 1)] = fma(-l1, l10, Lk[QPB_LIDX(r, c + 1)]) * r2;
+        }
+#pragma unroll
+        for (int r = c + 2; r < 8; ++r)
+#pragma unroll
+            for (int cc = c + 2; cc <= r; ++cc)
+                Lk[QPB_LIDX(r, cc)] = fma(-Lk[QPB_LIDX(r, c + 1)], Lk[QPB_LIDX(cc, c + 1)],
+                                          fma(-Lk[QPB_LIDX(r, c)], Lk[QPB_LIDX(cc, c)], Lk[QPB_LIDX(r, cc)]));
+    }
+#else
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const double ri = f_rsqrt(Lk[QPB_LIDX(c, c)]);
@@ -48,6 +78,7 @@ __device__ __forceinline__ void pf_factor8(double (&Lk)[36]) {
             for (int cc = c + 1; cc <= r; ++cc)
                 Lk[QPB_LIDX(r, cc)] = fma(-Lk[QPB_LIDX(r, c)], Lk[QPB_LIDX(cc, c)], Lk[QPB_LIDX(r, cc)]);
     }
+#endif
 }
 // Column c = lane & 7 of T = L^-1 from the factored block (every lane holds Lk; the lane dependence is in predicates
 // only, so the eight columns are computed side by side instead of one lane doing all 112 operations):
@@ -85,6 +116,20 @@ __device__ __forceinline__ void pf_store_lower8(double* M, int r0, int c0, const
         for (int c = 0; c <= r; c += 2)      // the odd tail writes one element of the (unused) upper part of the tile
             *reinterpret_cast<double2*>(Mb + r * ldi + c) =
                 make_double2(Lk[QPB_LIDX(r, c)], (c + 1 <= r) ? Lk[QPB_LIDX(r, c + 1)] : 0.0);
+}
+
+// ---- tile table of the trailing updates -----------------------------------------------------------------------------
+// The trailing tiles of step k are (i, j), k < j <= i < nts. In MIRRORED coordinates j' = nts-1-j, i' = nts-1-i they are
+// the leading triangle i' <= j' <= nts-2-k, so with the tiles enumerated as t' = j'(j'+1)/2 + i' the active ones of ANY
+// step of ANY order are the prefix [0, (nts-1-k)(nts-k)/2) of ONE table, whose last element is the chain warp's tile
+// (k+1, k+1). tab[t'] = (j' << 8) | i'. (The first version walked the triangle with while-loops: 8 % of all the
+// instructions of the three-per-SM forward kernel, profiles/r2z_source_hotspots_throughput.txt.)
+__host__ __device__ __forceinline__ int pf_tab_doubles(int nts) { return ((nts * (nts + 1)) / 2 + 3) >> 2; }
+__device__ __forceinline__ void pf_build_tab(int tabo, int nts) {
+    QPB_SMEM;
+    uint16_t* tab = reinterpret_cast<uint16_t*>(qsm + tabo);
+    for (int jp = threadIdx.x; jp < nts; jp += kNT)
+        for (int ip = 0; ip <= jp; ++ip) tab[(jp * (jp + 1)) / 2 + ip] = (uint16_t)((jp << 8) | ip);
 }
 
 // ---- the factorization --------------------------------------------------------------------------------------------
@@ -179,7 +224,7 @@ __device__ __forceinline__ void pf_chol_chain(int S, int nts, int kb0, int pan) 
 }
 
 template <bool kSetup>
-__device__ __noinline__ void pf_chol_update_t(int S, int nts, int kb0, int kend, int aug, int pan, double* Lg, int ln) {
+__device__ __noinline__ void pf_chol_update_t(int S, int nts, int kb0, int kend, int aug, int pan, int tabo, double* Lg, int ln) {
     QPB_SMEM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -237,24 +282,22 @@ __device__ __noinline__ void pf_chol_update_t(int S, int nts, int kb0, int kend,
             qsm[aug + r] = s0 + s1;
         }
         QPB_TICK1(45);                      // right-hand side rows
-        // ---- U_k: trailing tiles (i, j), k < j <= i, except the chain warp's (k+1, k+1); column-major order, dealt
-        // round-robin, four tiles (= four independent DMMA chains) in flight per warp
+        // ---- U_k: trailing tiles (i, j), k < j <= i, except the chain warp's (k+1, k+1) (= the last entry of the table
+        // prefix), dealt round-robin, four tiles (= four independent DMMA chains) in flight per warp
         {
-            int j = k + 1, p = (uw == 0) ? nuw : uw;         // (linear index 0 is the chain warp's tile)
-            while (j < nts && p >= nts - j) { p -= nts - j; ++j; }
+            const uint16_t* tab = reinterpret_cast<const uint16_t*>(qsm + tabo);
+            const int nact = ((nts - 1 - k) * (nts - k)) / 2 - 1;
 #pragma unroll 1
-            while (j < nts) {
+            for (int t0 = uw; t0 < nact; t0 += 4 * nuw) {
                 int ti[4], tj[4];
                 bool ok[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    ok[u] = j < nts;
-                    ti[u] = ok[u] ? j + p : ti[0];
-                    tj[u] = ok[u] ? j : tj[0];
-                    if (ok[u]) {
-                        p += nuw;
-                        while (j < nts && p >= nts - j) { p -= nts - j; ++j; }
-                    }
+                    const int t = t0 + u * nuw;
+                    ok[u] = t < nact;
+                    const int e = tab[ok[u] ? t : t0];
+                    ti[u] = nts - 1 - (e & 255);
+                    tj[u] = nts - 1 - (e >> 8);
                 }
                 double2 v[4];
                 double a0[4], a1[4], b0[4], b1[4];
@@ -284,18 +327,19 @@ __device__ __noinline__ void pf_chol_update_t(int S, int nts, int kb0, int kend,
     }
 }
 
-__device__ __forceinline__ void pf_chol_update(int S, int nts, int kb0, int aug, int pan) {
-    pf_chol_update_t<false>(S, nts, kb0, nts, aug, pan, nullptr, 0);
+__device__ __forceinline__ void pf_chol_update(int S, int nts, int kb0, int aug, int pan, int tabo) {
+    pf_chol_update_t<false>(S, nts, kb0, nts, aug, pan, tabo, nullptr, 0);
 }
 
-__device__ __forceinline__ void pf_chol(int S, int nts, int kb0, int aug, int pan) {
+// tabo: the tile table of pf_build_tab (any order >= nts)
+__device__ __forceinline__ void pf_chol(int S, int nts, int kb0, int aug, int pan, int tabo) {
     if (threadIdx.x < 32) pf_chol_chain(S, nts, kb0, pan);
-    else pf_chol_update(S, nts, kb0, aug, pan);
+    else pf_chol_update(S, nts, kb0, aug, pan, tabo);
 }
 // pre_factor_kkt flavour: block columns [kb0, kend) only, optional emission of the plain factor (see pf_chol_chain_t)
-__device__ __forceinline__ void pf_chol_setup(int S, int nts, int kb0, int kend, int aug, int pan, double* Lg, int ln) {
+__device__ __forceinline__ void pf_chol_setup(int S, int nts, int kb0, int kend, int aug, int pan, int tabo, double* Lg, int ln) {
     if (threadIdx.x < 32) pf_chol_chain_t<true>(S, nts, kb0, kend, pan, Lg, ln);
-    else pf_chol_update_t<true>(S, nts, kb0, kend, aug, pan, Lg, ln);
+    else pf_chol_update_t<true>(S, nts, kb0, kend, aug, pan, tabo, Lg, ln);
 }
 
 // ---- substitutions (order n = 8 nts <= kNT: thread tid owns entry tid) ----------------------------------------------

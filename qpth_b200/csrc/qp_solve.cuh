@@ -44,12 +44,12 @@ __host__ __device__ inline FLayout fast_layout(const KDims& D, bool coop, bool p
     L.vec = coop ? after_s : L.Lp + D.lp;
     L.red = L.vec + (pf ? F_COUNT - 1 : F_COUNT) * L.vl;
     L.bar = L.red + kFastRed;
-    L.tab = L.bar + 2;                                       // tile table of the round-1 Cholesky (not in the pf layouts)
+    L.tab = L.bar + 2;                                       // tile table: round-1 Cholesky (kTabDoubles) / pf_build_tab
     return L;
 }
 __host__ __device__ inline size_t fast_smem_doubles(const KDims& D, bool coop, bool pf = false) {
     const FLayout L = fast_layout(D, coop, pf);
-    return (size_t)L.tab + (pf ? 0 : kTabDoubles);
+    return (size_t)L.tab + (pf ? qpb::pf::pf_tab_doubles(D.msp >> 3) : kTabDoubles);
 }
 
 struct FCtx {
@@ -128,6 +128,7 @@ __device__ __forceinline__ FCtx f_make_ctx(const KDims& D, int qp, const double*
         mbar_init(bar + 1, 1);
     }
     if (!kPF) build_tile_table(reinterpret_cast<uint16_t*>(qsm + C.L.tab), (D.msp - D.ep) >> 3, tid);
+    else qpb::pf::pf_build_tab(C.L.tab, D.msp >> 3);
     __syncthreads();
     C.lglobal = kCoop && kPF && (!kStageL || D.lp > s_doubles(D, true));
     if (kCoop && kPF && C.lglobal) {
@@ -228,7 +229,7 @@ __device__ __forceinline__ void f_factor_and_solve_pf(const KDims& D, FCtx& C) {
     _Pragma("unroll 1") for (int i = D.ep + tid; i < D.ms; i += kNT) qsm[C.L.LS + pf_rowoff(i) + i] += 1.0 / qsm[FV(F_D) + i];
     __syncthreads();
     if (D.ep > 0) pf_fwd(C.L.LS, D.msp, 0, D.ep >> 3, FV(F_AUG));
-    pf_chol(C.L.LS, D.msp >> 3, D.ep >> 3, FV(F_AUG), C.L.pan);
+    pf_chol(C.L.LS, D.msp >> 3, D.ep >> 3, FV(F_AUG), C.L.pan, C.L.tab);
     QPB_TICK(32);
     pf_diag(C.L.LS, D.msp, FV(F_AUG), FV(F_T0), FV(F_AUG));
     pf_bwd(C.L.LS, D.msp, FV(F_AUG), FV(F_W));
