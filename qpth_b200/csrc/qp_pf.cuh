@@ -287,15 +287,22 @@ __device__ __noinline__ void pf_chol_update_t(int S, int nts, int kb0, int kend,
         {
             const uint16_t* tab = reinterpret_cast<const uint16_t*>(qsm + tabo);
             const int nact = ((nts - 1 - k) * (nts - k)) / 2 - 1;
+            // a warp takes FOUR CONSECUTIVE table entries at a time: they mostly lie in one tile column, whose panel
+            // fragment (the B operand) is then loaded once
+#ifndef QPB_PF_CHUNK
+#define QPB_PF_CHUNK 1     // A/B knob (profiles/r2y_chunk_sweepbar_ab.txt): 0 round-robin, 1 always four consecutive entries (best:
+                           // C2 latency 503 -> 489 us, B = 8192 15.45 -> 15.11 ms, C4 1727 -> 1637 us), 2 consecutive when plenty
+#endif
+            const bool chunked = (QPB_PF_CHUNK == 1) || (QPB_PF_CHUNK == 2 && nact >= 8 * nuw);
+            const int su = chunked ? 1 : nuw;
 #pragma unroll 1
-            for (int t0 = uw; t0 < nact; t0 += 4 * nuw) {
+            for (int t0 = chunked ? 4 * uw : uw; t0 < nact; t0 += 4 * nuw) {
                 int ti[4], tj[4];
                 bool ok[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int t = t0 + u * nuw;
-                    ok[u] = t < nact;
-                    const int e = tab[ok[u] ? t : t0];
+                    ok[u] = t0 + u * su < nact;
+                    const int e = tab[ok[u] ? t0 + u * su : t0];
                     ti[u] = nts - 1 - (e & 255);
                     tj[u] = nts - 1 - (e >> 8);
                 }
@@ -306,9 +313,14 @@ __device__ __noinline__ void pf_chol_update_t(int S, int nts, int kb0, int kend,
                 for (int u = 0; u < 4; ++u) {
                     cp[u] = M + pf_rowoff(8 * ti[u] + g) + 8 * tj[u] + 2 * q;
                     const double* pa = P + (8 * ti[u] + g) * kPanLd + q;
-                    const double* pb = P + (8 * tj[u] + g) * kPanLd + q;
                     v[u] = *reinterpret_cast<const double2*>(cp[u]);
-                    a0[u] = pa[0]; a1[u] = pa[4]; b0[u] = pb[0]; b1[u] = pb[4];
+                    a0[u] = pa[0]; a1[u] = pa[4];
+                    if (u == 0 || tj[u] != tj[u - 1]) {      // (warp-uniform)
+                        const double* pb = P + (8 * tj[u] + g) * kPanLd + q;
+                        b0[u] = pb[0]; b1[u] = pb[4];
+                    } else {
+                        b0[u] = b0[u - 1]; b1[u] = b1[u - 1];
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
@@ -345,33 +357,42 @@ __device__ __forceinline__ void pf_chol_setup(int S, int nts, int kb0, int kend,
 // ---- substitutions (order n = 8 nts <= kNT: thread tid owns entry tid) ----------------------------------------------
 // Running right-hand side over block columns [kb, ke):  b_i -= P_ik b_k  for every row below block k. In place.
 // Ends with a block barrier; afterwards b holds the running right-hand side of ALL rows.
+// Only the warps that own rows (tid < n) run the sweep, on a named barrier of their own (id 3); the others go straight
+// to the closing block barrier.
 __device__ __noinline__ void pf_fwd(int S, int n, int kb, int ke, int b) {
     QPB_SMEM;
     const int tid = threadIdx.x;
     const double* M = qsm + S;
     const bool mine = tid < n;
-    const int ro = pf_rowoff(mine ? tid : 0);
-    double acc = mine ? qsm[b + tid] : 0.0;
-    double row[8];
-    if (mine && tid >= 8 * kb + 8 && kb < ke) f_ld8(M + ro + 8 * kb, row);
+#ifndef QPB_PF_SWEEPBAR
+#define QPB_PF_SWEEPBAR 0  // A/B knob: 1 = the sweeps synchronise the row-owning warps only (named barrier 3): measured slightly
+                           // SLOWER than the whole-block barrier (r2y: 752 vs 741 us, 15.58 vs 15.46 ms); 0 = the whole block
+#endif
+    const int nwp = QPB_PF_SWEEPBAR ? ((n + 31) >> 5) : (kNT / 32);   // participating warps
+    if ((tid >> 5) < nwp) {
+        const int ro = pf_rowoff(mine ? tid : 0);
+        double acc = mine ? qsm[b + tid] : 0.0;
+        double row[8];
+        if (mine && tid >= 8 * kb + 8 && kb < ke) f_ld8(M + ro + 8 * kb, row);
 #pragma unroll 1
-    for (int k = kb; k < ke; ++k) {
-        const int k0 = 8 * k;
-        if (mine && tid >= k0 + 8) {
-            double y[8];
-            f_ld8(qsm + b + k0, y);
-            double s1 = row[1] * y[1];
-            acc = fma(-row[0], y[0], acc); s1 = fma(row[3], y[3], s1);
-            acc = fma(-row[2], y[2], acc); s1 = fma(row[5], y[5], s1);
-            acc = fma(-row[4], y[4], acc); s1 = fma(row[7], y[7], s1);
-            acc = fma(-row[6], y[6], acc);
-            acc -= s1;
-            if (tid < k0 + 16) qsm[b + tid] = acc;           // block k+1 becomes final
-            else if (k + 1 < ke) f_ld8(M + ro + k0 + 8, row);  // next step's P row (static data: no hazard)
+        for (int k = kb; k < ke; ++k) {
+            const int k0 = 8 * k;
+            if (mine && tid >= k0 + 8) {
+                double y[8];
+                f_ld8(qsm + b + k0, y);
+                double s1 = row[1] * y[1];
+                acc = fma(-row[0], y[0], acc); s1 = fma(row[3], y[3], s1);
+                acc = fma(-row[2], y[2], acc); s1 = fma(row[5], y[5], s1);
+                acc = fma(-row[4], y[4], acc); s1 = fma(row[7], y[7], s1);
+                acc = fma(-row[6], y[6], acc);
+                acc -= s1;
+                if (tid < k0 + 16) qsm[b + tid] = acc;           // block k+1 becomes final
+                else if (k + 1 < ke) f_ld8(M + ro + k0 + 8, row);  // next step's P row (static data: no hazard)
+            }
+            named_bar_sync(3, 32 * nwp);
         }
-        __syncthreads();
+        if (mine && tid >= 8 * ke + 8 && kb < ke) qsm[b + tid] = acc;   // rows not yet published (partial sweeps only)
     }
-    if (mine && tid >= 8 * ke + 8 && kb < ke) qsm[b + tid] = acc;   // rows not yet published (partial sweeps only)
     __syncthreads();
 }
 
@@ -417,40 +438,44 @@ __device__ __noinline__ void pf_bwd(int S, int n, int c, int w) {
     const int tid = threadIdx.x;
     const double* M = qsm + S;
     const int nts = n >> 3;
-    double acc = (tid < n) ? qsm[c + tid] : 0.0;
-    if (tid >= n - 8 && tid < n) qsm[w + tid] = acc;
-    double col[8];
-    {
-        const int i = nts - 1, ldi = 8 * i + 12;
-        const double* Pc = M + (32 * i + 64) * i + tid;
-        if (tid < 8 * i) {
+    const int nwp = QPB_PF_SWEEPBAR ? ((n + 31) >> 5) : (kNT / 32);   // participating warps (see pf_fwd)
+    if ((tid >> 5) < nwp) {
+        double acc = (tid < n) ? qsm[c + tid] : 0.0;
+        if (tid >= n - 8 && tid < n) qsm[w + tid] = acc;
+        double col[8];
+        {
+            const int i = nts - 1, ldi = 8 * i + 12;
+            const double* Pc = M + (32 * i + 64) * i + tid;
+            if (tid < 8 * i) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) col[r] = Pc[r * ldi];
+                for (int r = 0; r < 8; ++r) col[r] = Pc[r * ldi];
+            }
+        }
+        named_bar_sync(3, 32 * nwp);
+#pragma unroll 1
+        for (int i = nts - 1; i > 0; --i) {
+            const int i0 = 8 * i;
+            if (tid < i0) {
+                double y[8];
+                f_ld8(qsm + w + i0, y);
+                double s1 = col[1] * y[1];
+                acc = fma(-col[0], y[0], acc); s1 = fma(col[3], y[3], s1);
+                acc = fma(-col[2], y[2], acc); s1 = fma(col[5], y[5], s1);
+                acc = fma(-col[4], y[4], acc); s1 = fma(col[7], y[7], s1);
+                acc = fma(-col[6], y[6], acc);
+                acc -= s1;
+                if (tid >= i0 - 8) qsm[w + tid] = acc;           // block i-1 becomes final
+                else {
+                    const int im = i - 1, ldm = 8 * im + 12;
+                    const double* Pc = M + (32 * im + 64) * im + tid;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) col[r] = Pc[r * ldm];
+                }
+            }
+            named_bar_sync(3, 32 * nwp);
         }
     }
     __syncthreads();
-#pragma unroll 1
-    for (int i = nts - 1; i > 0; --i) {
-        const int i0 = 8 * i;
-        if (tid < i0) {
-            double y[8];
-            f_ld8(qsm + w + i0, y);
-            double s1 = col[1] * y[1];
-            acc = fma(-col[0], y[0], acc); s1 = fma(col[3], y[3], s1);
-            acc = fma(-col[2], y[2], acc); s1 = fma(col[5], y[5], s1);
-            acc = fma(-col[4], y[4], acc); s1 = fma(col[7], y[7], s1);
-            acc = fma(-col[6], y[6], acc);
-            acc -= s1;
-            if (tid >= i0 - 8) qsm[w + tid] = acc;           // block i-1 becomes final
-            else {
-                const int im = i - 1, ldm = 8 * im + 12;
-                const double* Pc = M + (32 * im + 64) * im + tid;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) col[r] = Pc[r * ldm];
-            }
-        }
-        __syncthreads();
-    }
 }
 
 // Full solve with a product-form factor: rhs (destroyed) -> out. y: scratch. rhs, y, out distinct.
