@@ -63,6 +63,34 @@ TRACE = False     # keep per-iteration residual traces on st.trace even when ver
 # Set qpth_b200.qp.MODE (or QPTH_B200_MODE) before the call; results are identical bit for bit.
 import os as _os
 MODE = _os.environ.get("QPTH_B200_MODE", "auto")
+# The reference's DEFAULT options (check_Q_spd=True, verbose=0) make every forward read two flags back from the device
+# before it returns ('Q is not SPD.' qp.py:81-85; the inaccurate-solution banner batch.py:205-206): one blocking host
+# read per call, which caps a training loop at ~72k QPs/s on a B200 (profiles/r2z_bench.json, e2e.default_options)
+# where the asynchronous options reach 230k. LAZY_CHECKS = True keeps the diagnostics but DEFERS them: the flags are
+# copied to pinned host memory asynchronously and examined at the next QPFunction call, in backward, or by
+# flush_checks() - the error / banner then refers to an EARLIER call. Off by default: the reference raises at once.
+LAZY_CHECKS = _os.environ.get("QPTH_B200_LAZY_CHECKS", "0") == "1"
+_pending = []
+import threading as _threading
+_pending_lock = _threading.Lock()      # forward runs on the caller's thread, backward on the autograd engine's
+
+
+def flush_checks(wait=True):
+    """Examine the deferred diagnostics (LAZY_CHECKS) of earlier forward calls; wait=False only those already on the host."""
+    while True:
+        with _pending_lock:
+            if not _pending:
+                return
+            ev, host, chk, banner = _pending[0]
+            if not wait and not ev.query():
+                return
+            _pending.pop(0)
+        ev.synchronize()
+        bad_spd, inacc = host.tolist()
+        if banner and inacc:
+            print(INACC_ERR)
+        if chk and bad_spd:
+            raise RuntimeError('Q is not SPD. (reported by a deferred check, qpth_b200.qp.LAZY_CHECKS)')
 
 
 class QPSolvers(Enum):
@@ -95,6 +123,8 @@ def solve_forward(Q_, p_, G_, h_, A_, b_, eps=1e-12, verbose=0, notImprovedLim=3
     # rank errors exactly as expandParam raises them (util.py:44-50), then every trailing dimension / batch size:
     # pure host logic, done before anything touches the device
     nBatch, nz, nineq, neq = check_shapes(Q_, p_, G_, h_, A_, b_)
+    if _pending:
+        flush_checks(wait=False)
     assert neq > 0 or nineq > 0                         # qp.py:89
     if nineq == 0:
         raise RuntimeError('qpth_b200: nineq == 0 is not supported (the reference unpacks G.size() at qp.py:87)')
@@ -148,11 +178,21 @@ def solve_forward(Q_, p_, G_, h_, A_, b_, eps=1e-12, verbose=0, notImprovedLim=3
         # 'Q is not SPD.' (qp.py:81-85) and the inaccurate-solution banner, printed iff
         # best resids max > 1 and verbose >= 0 (batch.py:141-142,205-206).
         if check_Q_spd or verbose >= 0:
-            bad_spd, inacc = torch.stack([spd.any(), (st.best_resid.max() > 1.)]).tolist()
-            if check_Q_spd and bad_spd:
-                raise RuntimeError('Q is not SPD.')
-            if verbose >= 0 and inacc:
-                print(INACC_ERR)
+            flags = torch.stack([spd.any(), (st.best_resid.max() > 1.)])
+            if LAZY_CHECKS:
+                # the two flags travel to a pinned host buffer asynchronously; they are examined (and 'Q is not SPD.' raised,
+                # the banner printed) at the next QPFunction call, in this call's backward, or by flush_checks()
+                host = torch.empty(2, dtype=flags.dtype).pin_memory()
+                host.copy_(flags, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                _pending.append((ev, host, bool(check_Q_spd), verbose >= 0))
+            else:
+                bad_spd, inacc = flags.tolist()
+                if check_Q_spd and bad_spd:
+                    raise RuntimeError('Q is not SPD.')
+                if verbose >= 0 and inacc:
+                    print(INACC_ERR)
         if verbose == 1:
             # batch.py:115-117: per-iteration batch means; a QP that has already stopped contributes
             # the values of its last iteration (in the reference every QP runs every iteration)
@@ -168,6 +208,8 @@ def solve_forward(Q_, p_, G_, h_, A_, b_, eps=1e-12, verbose=0, notImprovedLim=3
 
 def solve_backward(st, dl_dzhat, mean_flags, want):
     """QPFunctionFn.backward on the device. mean_flags / want: 6-tuples for (Q,p,G,h,A,b)."""
+    if _pending:
+        flush_checks(wait=False)
     lib = _lib.load()
     plan, B, device = st.plan, st.nBatch, st.device
     nz, nineq, neq = plan.nz, plan.nineq, plan.neq

@@ -91,3 +91,30 @@ def test_lower_triangle_strip_copies():
         copy_lower_(back, d, band=band)
         torch.cuda.synchronize()
         assert torch.equal(torch.tril(back), torch.tril(h))
+
+
+def test_lazy_checks_defer_the_flag_read(capsys):
+    """qp.LAZY_CHECKS: the SPD / inaccuracy flags are examined later (flush_checks), not inside forward."""
+    import torch
+    from qpth_b200 import QPFunction, qp as qpmod
+    from qpth_b200.problems import random_qp_batch
+    pr = random_qp_batch(4, 12, 8, 0, seed=5)
+    t = {k: torch.tensor(pr[k], dtype=torch.float64, device="cuda:0") for k in ("Q", "p", "G", "h")}
+    e = torch.Tensor().to("cuda:0").double()
+    bad = t["Q"].clone(); bad[1] = -bad[1]                     # not SPD
+    old = qpmod.LAZY_CHECKS
+    try:
+        qpmod.LAZY_CHECKS = True
+        QPFunction()(bad, t["p"], t["G"], t["h"], e, e)        # returns without raising
+        with pytest.raises(RuntimeError, match="Q is not SPD"):
+            qpmod.flush_checks()
+        assert not qpmod._pending
+        z = QPFunction()(t["Q"], t["p"], t["G"], t["h"], e, e)  # a good problem: nothing pending after the flush
+        qpmod.flush_checks()
+        assert bool(torch.isfinite(z).all())
+        qpmod.LAZY_CHECKS = False
+        with pytest.raises(RuntimeError, match="Q is not SPD"):
+            QPFunction()(bad, t["p"], t["G"], t["h"], e, e)
+    finally:
+        qpmod.LAZY_CHECKS = old
+        qpmod._pending.clear()
