@@ -1,5 +1,7 @@
 #!/bin/bash
-TAG=${1:-r2y}
+# A/B of kernel build variants on ONE box, two repetitions each (the method behind profiles/r2y_chunk_sweepbar_ab.txt):
+# build them with scripts/build_variants.sh real "NAME:-DFLAG=..." ..., list the NAMEs in the loop below.
+TAG=${1:-ab}
 O=gpurun_out/$TAG
 mkdir -p $O
 : > $O/summary.txt
