@@ -1,10 +1,13 @@
 // qpth_b200 — sm_100a kernels + C ABI for the batched differentiable QP hot path.
 //
 // Mapping to the reference (locuslab/qpth @ 528e9f6, citations relative to /root/reference):
-//   k_setup     <- pre_factor_kkt            qpth/solvers/pdipm/batch.py:375-429  (+ SPD check qp.py:81-85)
-//   k_forward   <- forward (PDIPM loop)      qpth/solvers/pdipm/batch.py:47-207   (+ get_step :210-213)
-//   k_backward  <- QPFunctionFn.backward     qpth/qp.py:128-182
-//   k_solve_kkt <- factor_kkt + solve_kkt    qpth/solvers/pdipm/batch.py:435-470, 349-372
+//   k_setup*    <- pre_factor_kkt            qpth/solvers/pdipm/batch.py:375-429  (+ SPD check qp.py:81-85)
+//   k_forward*  <- forward (PDIPM loop)      qpth/solvers/pdipm/batch.py:47-207   (+ get_step :210-213)
+//   k_kkt_fast<true> / k_solve_kkt<..,true>  <- QPFunctionFn.backward     qpth/qp.py:128-182
+//   k_kkt_fast<false> / k_solve_kkt          <- factor_kkt + solve_kkt    qpth/solvers/pdipm/batch.py:435-470, 349-372
+// Kernel families (chosen by qpb200_plan_init, see include/qpth_b200.h): product form (qp_solve.cuh + qp_pf.cuh; the
+// default wherever the reduced system has order <= 256), round-1 shared-memory kernels (QPB200_PF=0), generic kernels
+// below (one warp per QP for tiny shapes; global scratch for shapes nothing else fits).
 //
 // Formulation: with Q = L L^T the variables are whitened, x~ = L^T x, so
 //   W = [A; G] L^-T            (rows 0..ep-1: equality rows, zero-padded to a multiple of 8; then G rows)
