@@ -133,22 +133,24 @@ __device__ __forceinline__ double tri_norm2_partial(const double* Lp, int n, con
 
 // Block-wide reductions of N values. `red` is shared scratch of >= N * kRedStride doubles (up to 16 warps).
 constexpr int kRedStride = 16;
-// Every thread returns with the reduced values. Two barriers per call.
-template <int N, bool kMin>
+// Every thread returns with the reduced values. Two barriers per call (one with kGuard = false).
+template <int N, bool kMin, bool kGuard = true, int kStride = kRedStride>
 __device__ __forceinline__ void block_reduce(double (&v)[N], double* red, int tid, int nt) {
     const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
 #pragma unroll
     for (int k = 0; k < N; ++k) v[k] = kMin ? warp_min(v[k]) : warp_sum(v[k]);
-    __syncthreads();   // protect scratch from the previous call's readers
+    // protect scratch from the previous call's readers (kGuard = false: the caller alternates between two scratch areas,
+    // so the previous call's readers use the other one and the call before that is fenced by the previous call's barrier)
+    if (kGuard) __syncthreads();
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) red[k * kRedStride + warp] = v[k];
+        for (int k = 0; k < N; ++k) red[k * kStride + warp] = v[k];
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         double a = kMin ? INFINITY : 0.0;
-        for (int w = 0; w < nw; ++w) a = kMin ? fmin(a, red[k * kRedStride + w]) : a + red[k * kRedStride + w];
+        for (int w = 0; w < nw; ++w) a = kMin ? fmin(a, red[k * kStride + w]) : a + red[k * kStride + w];
         v[k] = a;
     }
 }

@@ -931,6 +931,56 @@ __device__ __noinline__ void f_matvec_rows2(int W, int ld, int rows, int cols, i
 __device__ __noinline__ void f_matvec_rows1(int W, int ld, int rows, int cols, int x1, int y1) {
     f_matvec_rows_impl<false>(W, ld, rows, cols, x1, 0, y1, 0);
 }
+#ifndef QPB_MVCOLS2
+#define QPB_MVCOLS2 0    // A/B knob: 1 = f_matvec_cols with two columns per thread (LDS.128) and as many row groups as fit
+#endif
+#if QPB_MVCOLS2
+// out[c] = sa * a[c] + sgn * (W^T v)[c] (+ b[c] if b >= 0). A warp owns 16 columns: lane = (row group g, column pair cq),
+// one LDS.128 per row (a quarter-warp reads 128 contiguous bytes: no bank conflicts), the four row groups are summed with
+// two shuffles. Half the shared-memory loads of the one-column-per-thread version and no partial-sum vectors (p0, p1 unused).
+__device__ __noinline__ void f_matvec_cols(int W, int ld, int rows, int cols, int v, int p0, int p1, int out,
+                                           int a, double sa, int b, double sgn) {
+    QPB_SMEM;
+    (void)p0; (void)p1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 3, cq = lane & 7;
+#pragma unroll 1
+    for (int c0 = 0; c0 < cols; c0 += 16 * (kNT / 32)) {     // warp-uniform trip count
+        const int c = c0 + 16 * warp + 2 * cq;
+        const bool okc = c < cols;
+        const double* Wp = qsm + W + (okc ? c : 0);
+        double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+        int r = g;
+#pragma unroll 2
+        for (; r + 4 < rows; r += 8) {
+            const double2 w0 = *reinterpret_cast<const double2*>(Wp + r * ld);
+            const double2 w1 = *reinterpret_cast<const double2*>(Wp + (r + 4) * ld);
+            const double v0 = qsm[v + r], v1 = qsm[v + r + 4];
+            s0 = fma(w0.x, v0, s0); s1 = fma(w0.y, v0, s1);
+            t0 = fma(w1.x, v1, t0); t1 = fma(w1.y, v1, t1);
+        }
+        if (r < rows) {
+            const double2 w0 = *reinterpret_cast<const double2*>(Wp + r * ld);
+            const double v0 = qsm[v + r];
+            s0 = fma(w0.x, v0, s0); s1 = fma(w0.y, v0, s1);
+        }
+        s0 += t0; s1 += t1;
+        __syncwarp();
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 8);  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        if (g == 0 && okc) {
+            double r0 = sa * qsm[a + c] + sgn * s0;
+            if (b >= 0) r0 += qsm[b + c];
+            qsm[out + c] = r0;
+            if (c + 1 < cols) {
+                double r1 = sa * qsm[a + c + 1] + sgn * s1;
+                if (b >= 0) r1 += qsm[b + c + 1];
+                qsm[out + c + 1] = r1;
+            }
+        }
+    }
+    __syncthreads();
+}
+#else
 // out[c] = a[c] + sgn * (W^T v)[c] (+ b[c] if b >= 0). Two row groups, partial sums in p0/p1.
 __device__ __noinline__ void f_matvec_cols(int W, int ld, int rows, int cols, int v, int p0, int p1, int out,
                                            int a, double sa, int b, double sgn) {
@@ -966,6 +1016,8 @@ __device__ __noinline__ void f_matvec_cols(int W, int ld, int rows, int cols, in
     }
     __syncthreads();
 }
+
+#endif
 
 // || L x ||^2 partial sums (packed lower L in shared memory): 4 lanes per row, rows paired (r, n-1-r) so that every
 // lane group streams n + 1 entries. Returns this thread's partial (lane l == 0 of a group); sum over the block after.
@@ -1163,17 +1215,21 @@ __device__ __noinline__ double g_tri_norm2(const double* __restrict__ Lg, int n,
     return acc;
 }
 
+#ifndef QPB_RED1
+#define QPB_RED1 0       // A/B knob: 1 = one barrier per block reduction (callers alternate between two scratch halves)
+#endif
+constexpr int kFastStride = (kNT / 32 <= 8) ? 8 : 16;       // per-value stride of the fast kernels' reduction scratch
 __device__ __noinline__ void f_reduce_sum4(double (&v)[4], int red) {
     QPB_SMEM;
-    block_reduce<4, false>(v, qsm + red, (int)threadIdx.x, kNT);
+    block_reduce<4, false, !QPB_RED1, kFastStride>(v, qsm + red, (int)threadIdx.x, kNT);
 }
 __device__ __noinline__ void f_reduce_sum2(double (&v)[2], int red) {
     QPB_SMEM;
-    block_reduce<2, false>(v, qsm + red, (int)threadIdx.x, kNT);
+    block_reduce<2, false, !QPB_RED1, kFastStride>(v, qsm + red, (int)threadIdx.x, kNT);
 }
 __device__ __noinline__ void f_reduce_min2(double (&v)[2], int red) {
     QPB_SMEM;
-    block_reduce<2, true>(v, qsm + red, (int)threadIdx.x, kNT);
+    block_reduce<2, true, !QPB_RED1, kFastStride>(v, qsm + red, (int)threadIdx.x, kNT);
 }
 
 }  // namespace fast

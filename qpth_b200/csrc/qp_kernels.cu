@@ -1310,6 +1310,11 @@ int qpb200_plan_init(int nz, int nineq, int neq, qpb200_plan* plan) {
             plan->pf_threads = (plan->pf_global && msp > 128 && !(e512 != nullptr && e512[0] == '0')) ? 512 : 256;
             // experiment knob: "2" = also the RESIDENT forward kernel at 512 threads (backward / solve_kkt stay at 256)
             if (!plan->pf_global && e512 != nullptr && e512[0] == '2') plan->pf_threads = 512;
+            // the 512-thread build keeps a wider reduction scratch (16 warps): its layout ends 64 doubles later
+            if (plan->pf_threads == 512) {
+                plan->pf_smem_bytes += 512;
+                if (plan->pf_smem_bytes > kMaxSmem) { plan->pf_threads = 256; plan->pf_smem_bytes -= 512; }
+            }
             plan->K_elems = (int64_t)qpb::pf::pf_elems(msp >> 3);
             plan->solve_scratch_elems = 0;                   // the factor lives in shared memory: no per-QP global workspace
             // pre_factor_kkt on the same machinery (k_setup_pf) whenever its shared memory fits

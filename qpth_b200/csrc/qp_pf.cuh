@@ -243,6 +243,42 @@ __device__ __noinline__ void pf_chol_update_t(int S, int nts, int kb0, int kend,
             const double bT0 = (q <= g) ? M[rg + q] : 0.0, bT1 = (q + 4 <= g) ? M[rg + q + 4] : 0.0;   // T[g][q], T[g][q+4]
             const double bP0 = (g <= q) ? M[rq] : 0.0, bP1 = (g <= q + 4) ? M[rq + ld4] : 0.0;        // T[q][g], T[q+4][g]
             // ---- S_k: panel tiles (i, k), i > k, dealt round-robin
+#ifndef QPB_PF_PANEL2
+#define QPB_PF_PANEL2 0    // A/B knob: 1 = two panel tiles in flight per warp
+#endif
+#if QPB_PF_PANEL2
+#pragma unroll 1
+            for (int i = k + 1 + uw; i < nts; i += 2 * nuw) {
+                const int i2 = i + nuw;
+                const bool two = i2 < nts;                   // (warp-uniform)
+                const int r1 = 8 * i + g, r2 = 8 * (two ? i2 : i) + g;
+                double* row1 = M + pf_rowoff(r1) + k0;
+                double* row2 = M + pf_rowoff(r2) + k0;
+                const double a10 = row1[q], a11 = row1[q + 4], a20 = row2[q], a21 = row2[q + 4];
+                double d0 = 0.0, d1 = 0.0, f0 = 0.0, f1 = 0.0;
+                dmma884(d0, d1, a10, bT0);
+                if (two) dmma884(f0, f1, a20, bT0);
+                dmma884(d0, d1, a11, bT1);
+                if (two) dmma884(f0, f1, a21, bT1);
+                if (kSetup && Lg != nullptr) {
+                    if (r1 < ln) { double* lrow = Lg + ((int64_t)r1 * (r1 + 1)) / 2 + k0 + 2 * q; lrow[0] = d0; lrow[1] = d1; }
+                    if (two && r2 < ln) { double* lrow = Lg + ((int64_t)r2 * (r2 + 1)) / 2 + k0 + 2 * q; lrow[0] = f0; lrow[1] = f1; }
+                }
+                double* pl1 = P + ((i == k + 1) ? (8 * nts + g) : r1) * kPanLd;
+                double* pl2 = P + r2 * kPanLd;               // (i2 > k + 1 always)
+                *reinterpret_cast<double2*>(pl1 + 2 * q) = make_double2(d0, d1);
+                if (two) *reinterpret_cast<double2*>(pl2 + 2 * q) = make_double2(f0, f1);
+                __syncwarp();
+                const double la0 = pl1[q], la1 = pl1[q + 4], lb0 = pl2[q], lb1 = pl2[q + 4];
+                double e0 = 0.0, e1 = 0.0, h0 = 0.0, h1 = 0.0;
+                dmma884(e0, e1, la0, bP0);
+                if (two) dmma884(h0, h1, lb0, bP0);
+                dmma884(e0, e1, la1, bP1);
+                if (two) dmma884(h0, h1, lb1, bP1);
+                *reinterpret_cast<double2*>(row1 + 2 * q) = make_double2(e0, e1);
+                if (two) *reinterpret_cast<double2*>(row2 + 2 * q) = make_double2(h0, h1);
+            }
+#else
 #pragma unroll 1
             for (int i = k + 1 + uw; i < nts; i += nuw) {
                 const int r = 8 * i + g;
@@ -265,6 +301,7 @@ __device__ __noinline__ void pf_chol_update_t(int S, int nts, int kb0, int kend,
                 dmma884(e0, e1, la1, bP1);
                 *reinterpret_cast<double2*>(row + 2 * q) = make_double2(e0, e1);
             }
+#endif
         }
         if (k < 16) QPB_TICK1(64 + k);      // S_k
         named_bar_sync(2, kNT);                               // every panel row of this step is in the scratch (the chain warp's too), every P_ik in place

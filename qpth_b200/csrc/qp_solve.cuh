@@ -18,7 +18,7 @@ using namespace qpb::fast;
 enum FVec { F_PT = 0, F_XT, F_RXT, F_S, F_V, F_RV, F_HW, F_W, F_DSA, F_DS, F_D, F_BXT, F_BS, F_BV, F_HB,
             F_DINVL, F_AUG, F_T0, F_T1, F_DINV, F_COUNT };
 
-constexpr int kFastRed = 4 * kRedStride;      // reduction scratch of the fast kernels (block_reduce<4>, up to 16 warps)
+constexpr int kFastRed = (QPB_RED1 ? 2 : 1) * 4 * qpb::fast::kFastStride;   // reduction scratch of the fast kernels (block_reduce<4>, up to 16 warps; two halves with QPB_RED1)
 struct FLayout {              // offsets in doubles into the dynamic shared array
     int W, LS, Lp, vec, red, bar, tab, pan;
     int vl;
@@ -269,6 +269,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
     __syncthreads();
 #endif
     FCtx C = f_make_ctx<kCoop, kPF>(D, qp, Lfac, Wfac, Kfac, sF);
+    int rtog = 0;                                               // which half of the reduction scratch the next block reduction uses
     QPB_TICK(0);
     const int pt = FV(F_PT), xt = FV(F_XT), rxt = FV(F_RXT), s = FV(F_S), v = FV(F_V), rv = FV(F_RV),
               hW = FV(F_HW), w = FV(F_W), dsa = FV(F_DSA), ds = FV(F_DS), d = FV(F_D), hb = FV(F_HB),
@@ -317,7 +318,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
                 mn[1] = fmin(mn[1], wi);
             }
         }
-        f_reduce_min2(mn, C.L.red);
+        f_reduce_min2(mn, C.L.red + rtog); rtog ^= (QPB_RED1 ? 4 * qpb::fast::kFastStride : 0);
         _Pragma("unroll 1") for (int i = ep + tid; i < ms; i += kNT) {               // slacks and duals >= 1 (batch.py:77-87)
             if (mn[0] < 0.0) qsm[s + i] -= mn[0] - 1.0;
             if (mn[1] < 0.0) qsm[v + i] -= mn[1] - 1.0;
@@ -347,7 +348,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         QPB_TICK(6);
         acc[2] = kCoop ? g_tri_norm2(C.Lg, n, rxt) : f_tri_norm2(C.L.Lp, n, rxt);
         QPB_TICK(7);
-        f_reduce_sum4(acc, C.L.red);
+        f_reduce_sum4(acc, C.L.red + rtog); rtog ^= (QPB_RED1 ? 4 * qpb::fast::kFastStride : 0);
         QPB_TICK(8);
         const double mu = fabs(acc[3] / dm);
         const double resid = sqrt(acc[1]) + sqrt(acc[0]) + sqrt(acc[2]) + dm * mu;
@@ -388,7 +389,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
             mn[0] = fmin(mn[0], step_candidate(qsm[v + i], dz));
             mn[1] = fmin(mn[1], step_candidate(qsm[s + i], dsi));
         }
-        f_reduce_min2(mn, C.L.red);
+        f_reduce_min2(mn, C.L.red + rtog); rtog ^= (QPB_RED1 ? 4 * qpb::fast::kFastStride : 0);
         {
             const double alpha = fmin(fmin(f_step_fix(mn[0]), f_step_fix(mn[1])), 1.0);
             double sm[2] = {0.0, 0.0};
@@ -396,7 +397,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
                 sm[0] = fma(qsm[s + i] + alpha * qsm[dsa + i], qsm[v + i] + alpha * qsm[w + i], sm[0]);
                 sm[1] = fma(qsm[s + i], qsm[v + i], sm[1]);
             }
-            f_reduce_sum2(sm, C.L.red);
+            f_reduce_sum2(sm, C.L.red + rtog); rtog ^= (QPB_RED1 ? 4 * qpb::fast::kFastStride : 0);
             const double sr = sm[0] / sm[1];
             const double sig = sr * sr * sr;
             // ---- corrector right-hand side (batch.py:170-181)
@@ -452,7 +453,7 @@ k_forward_fast(KDims D, const double* __restrict__ p, int64_t sp, const double* 
         QPB_TICK(14);
         mv_cols<kCoop>(D, C, w, t0, t1, hW, rxt, -1.0, -1, -1.0);     // dx~ = -r~x - W^T dv  (in hW)
         QPB_TICK(15);
-        f_reduce_min2(mn, C.L.red);
+        f_reduce_min2(mn, C.L.red + rtog); rtog ^= (QPB_RED1 ? 4 * qpb::fast::kFastStride : 0);
         {
             const double alpha = fmin(0.999 * fmin(f_step_fix(mn[0]), f_step_fix(mn[1])), 1.0);
             _Pragma("unroll 1") for (int i = tid; i < n; i += kNT) qsm[xt + i] = fma(alpha, qsm[hW + i], qsm[xt + i]);
