@@ -257,6 +257,8 @@ def e2e_leg(f, dev, rank, world, nsteps_req, warmup, dl, graphs=True):
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
+    import gc
+    gc.collect(); torch.cuda.synchronize()
     windows = []
     for _w in range(5):
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(NS + 1)]
@@ -423,7 +425,13 @@ def run_b200(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms = timed_window(args.steps, done, use_streams)
+    import gc
+    gc.collect(); torch.cuda.synchronize()            # (a collection inside the window can cudaFree / cudaFreeHost: tens of ms)
+    gc.disable()
+    try:
+        ms = timed_window(args.steps, done, use_streams)
+    finally:
+        gc.enable()
     clocks = sampler.stop() if sampler else None
     iters_mean = float((last_iters if launch_mode.startswith("cuda_graph") else f.last_solve().iters).float().mean())
     if world > 1:
@@ -589,16 +597,25 @@ def run_c4(dev):
             v.grad = None
         z = f(t["Q"], t["p"], t["G"], t["h"], e, e)
         z.backward(dl)
+    import gc
     settle(lambda i: one(), 5, 5, max_steps=100)      # until the caching allocator stops calling cudaMalloc (10-20 ms each)
     torch.cuda.synchronize()
+    # The legs before this one leave CUDA graphs with private pools and pinned host buffers behind; when Python's
+    # collector frees them in the middle of a window (cudaFree / cudaFreeHost block the host for tens of ms) the window
+    # measures that, not the solver: collect first, keep the collector off while timing.
+    gc.collect(); torch.cuda.synchronize()
+    gc.disable()
     reps, times = 10, []
-    for _w in range(3):                               # median of three windows of 10 steps
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            one()
-        e1.record(); torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1) / reps)
+    try:
+        for _w in range(5):                           # median of five windows of 10 steps
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                one()
+            e1.record(); torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / reps)
+    finally:
+        gc.enable()
     ms = float(np.median(times))
     return {"workload": "C4: cls-layer pattern batch=64 nz=200 nineq=200, shared Q,G,h, batched p, fwd+bwd", "ms_per_step": ms,
             "windows_ms_per_step": times,
