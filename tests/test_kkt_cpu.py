@@ -43,14 +43,21 @@ def test_kkt_resid_reg_matches_reference_when_present():
     from oracle import ref_runner
     if not ref_runner.available():
         pytest.skip("reference checkout not present (GPU box)")
+    import sys
     from qpth_b200 import kkt
-    _, rb = ref_runner.load()
-    p, eps = _problem(seed=1), 1e-7
-    ours = kkt.kkt_resid_reg(p["Q"], p["d"], p["G"], p["A"], eps, p["dx"], p["ds"], p["dz"], p["dy"], p["rx"], p["rs"], p["rz"], p["ry"])
-    ref = rb.kkt_resid_reg(p["Q"], torch.diag_embed(p["d"]), p["G"], p["A"], eps, p["dx"], p["ds"], p["dz"], p["dy"],
-                           p["rx"], p["rs"], p["rz"], p["ry"])
-    for a, b in zip(ours, ref):
-        assert float((a - b).abs().max()) < 1e-12
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "cvxpy" or k == "qpth" or k.startswith("qpth.")}
+    try:
+        _, rb = ref_runner.load()
+        p, eps = _problem(seed=1), 1e-7
+        ours = kkt.kkt_resid_reg(p["Q"], p["d"], p["G"], p["A"], eps, p["dx"], p["ds"], p["dz"], p["dy"], p["rx"], p["rs"], p["rz"], p["ry"])
+        ref = rb.kkt_resid_reg(p["Q"], torch.diag_embed(p["d"]), p["G"], p["A"], eps, p["dx"], p["ds"], p["dz"], p["dy"],
+                               p["rx"], p["rs"], p["rz"], p["ry"])
+        for a, b in zip(ours, ref):
+            assert float((a - b).abs().max()) < 1e-12
+    finally:                              # leave no reference modules (or the cvxpy stub) behind for the other tests
+        for k in [k for k in sys.modules if k == "cvxpy" or k == "qpth" or k.startswith("qpth.")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
 
 
 def test_golden_files_of_the_kkt_and_layer_tests_exist(golden_dir):
