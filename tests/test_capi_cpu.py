@@ -170,3 +170,61 @@ def test_shape_validation_raises_before_the_device_is_touched():
             QPFunction(verbose=-1)(*args)
     with pytest.raises(RuntimeError, match="Unexpected number of dimensions."):
         QPFunction(verbose=-1)(Q[None], p, G, h, A, b)
+
+
+def test_plan_invariants_over_a_shape_grid(lib):
+    """Every shape the planner accepts must get a launchable configuration: the shared memory of the family it selects
+    fits one CTA (227 KB opt-in limit), a promised co-residency (two / three QPs per SM) fits the SM's 228 KB including the
+    1 KB the driver reserves per CTA, the tile bookkeeping of the product-form kernels stays inside its table, and a
+    shape without a shared-memory variant has its global scratch sized. Shapes the kernels cannot take are refused by
+    plan_init (QPB200_ERR_TOO_LARGE), never accepted with an impossible plan."""
+    from qpth_b200 import _lib
+    cta_max, sm_total = 232448, 233472
+    seen = {"tiny": 0, "pf": 0, "pf3": 0, "pf2": 0, "global": 0, "refused": 0, "fast": 0}
+    for nz in (1, 2, 7, 8, 9, 16, 31, 32, 33, 50, 64, 100, 104, 105, 128, 150, 200, 256, 400):
+        for nineq in (0, 1, 5, 8, 24, 32, 50, 64, 100, 104, 105, 120, 128, 200, 256, 400):
+            for neq in (0, 1, 8, 10, 40, 100):
+                if nineq + neq == 0:
+                    continue
+                p = _lib.Plan()
+                rc = lib.qpb200_plan_init(nz, nineq, neq, ctypes.byref(p))
+                if rc != 0:
+                    assert rc == 4, (nz, nineq, neq, rc)
+                    seen["refused"] += 1
+                    continue
+                tag = (nz, nineq, neq)
+                assert p.neq_pad % 8 == 0 and p.neq_pad >= neq and p.ms == p.neq_pad + nineq, tag
+                assert p.ms_pad % 8 == 0 and 0 <= p.ms_pad - p.ms < 8, tag
+                assert p.L_elems >= nz * (nz + 1) // 2 and p.W_elems >= p.ms * nz and p.K_elems > 0, tag
+                assert p.threads in (32, 256) and p.pf_threads in (0, 256, 512), tag
+                if p.tiny:
+                    assert nz <= 32 and p.ms_pad <= 32 and p.threads == 32 and p.smem_resident == 1, tag
+                    assert 4 * (p.solve_smem_bytes + 1024) <= sm_total, tag       # (up to 16 per SM for the smallest)
+                    seen["tiny"] += 1
+                if p.pf:
+                    t = p.ms_pad // 8
+                    assert p.K_elems == 32 * t * t + 64 * t, tag
+                    assert p.pf_smem_bytes <= cta_max, tag
+                    assert p.pf_global in (0, 1) and (p.pf_threads == 256 or (p.pf_global == 1 and p.ms_pad > 128)), tag
+                    seen["pf"] += 1
+                    if p.pf2_ok:
+                        assert 2 * (p.pf2_smem_bytes + 1024) <= sm_total, tag
+                        seen["pf2"] += 1
+                    if p.pf3_ok:
+                        assert 3 * (p.pf3_smem_bytes + 1024) <= sm_total, tag
+                        seen["pf3"] += 1
+                    if p.setup_pf:
+                        assert p.setup_pf_smem_bytes <= cta_max, tag
+                else:
+                    assert (p.pf2_ok, p.pf3_ok, p.pf_two, p.pf_three) == (0, 0, 0, 0), tag
+                if p.coop_ok:
+                    assert 2 * (p.coop_smem_bytes + 1024) <= sm_total, tag
+                if p.smem_resident:
+                    assert p.solve_smem_bytes <= cta_max and p.solve_scratch_elems == 0, tag
+                elif not p.pf:
+                    assert p.solve_scratch_elems > 0 and p.setup_scratch_elems > 0, tag
+                    seen["global"] += 1
+                if not (p.pf and p.setup_pf) and p.smem_resident:
+                    assert p.setup_smem_bytes <= cta_max, tag
+                seen["fast"] += int(p.fast)
+    assert min(seen[k] for k in ("tiny", "pf", "pf2", "pf3", "global", "fast")) > 0, seen     # the grid reaches every family
