@@ -55,12 +55,14 @@ STALL_TOL = 1e-6
 # the minimum the latest is returned (1.0 restores the literal rule).
 BEST_TIE = 1.5
 TRACE = False     # keep per-iteration residual traces on st.trace even when verbose != 1 (diagnostics)
-# Kernel choice where a shape has both product-form variants (plan.pf2_ok, e.g. nz = nineq = 100):
+# Kernel choice where a shape has several product-form variants (plan.pf2_ok / plan.pf3_ok, e.g. nz = nineq = 100):
 #   "latency"    one QP per SM, W / chol(Q) / factor in shared memory: the shortest time for ONE batch <= #SMs;
-#   "throughput" two QPs per SM (W, chol(Q) read from L2): +23 % QPs/s once the GPU is full (a large batch, or several
-#                batches in flight on several streams), 1.24x the latency of a lone small batch (profiles/r2g_*);
+#   "throughput" three (else two) QPs per SM, W and chol(Q) read from L2: +34 % QPs/s once the GPU is full (a large
+#                batch, or several batches in flight on several streams), 1.5x the latency of a lone 128-QP batch
+#                (profiles/r2z_kernel_times.txt);
 #   "auto"       throughput when the batch alone exceeds the SM count, else latency.
-# Set qpth_b200.qp.MODE (or QPTH_B200_MODE) before the call; results are identical bit for bit.
+# Set qpth_b200.qp.MODE (or QPTH_B200_MODE) before the call. The variants differ only in the summation order of the
+# W / chol(Q) passes: results agree to ~1e-12 relative (tests/test_gpu_parity.py pins 1e-10), not bit for bit.
 import os as _os
 MODE = _os.environ.get("QPTH_B200_MODE", "auto")
 # The reference's DEFAULT options (check_Q_spd=True, verbose=0) make every forward read two flags back from the device
