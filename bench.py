@@ -285,7 +285,7 @@ def run_b200(args, rank, world, local_rank):
     from qpth_b200 import QPFunction, _lib
     from qpth_b200 import qp as qpmod
     # Every leg of this bench keeps several steps (batches) in flight on several CUDA streams, i.e. more QPs than the
-    # GPU has SMs: the library's throughput mode (two QPs per SM; qpth_b200.qp.MODE, a documented user switch whose
+    # GPU has SMs: the library's throughput mode (three QPs per SM at C2; qpth_b200.qp.MODE, a documented user switch whose
     # "auto" default picks it for any batch larger than the SM count). The single-stream figure (detail.serial_*) is
     # taken in latency mode (one QP per SM), the right choice for ONE 128-QP batch at a time.
     bench_mode = os.environ.get("QPB_BENCH_MODE", "throughput")
