@@ -58,3 +58,44 @@ def test_orders_beyond_shared_memory_vs_oracle(cfg):
         else:
             assert rel_rows(g, r, floor=1e-4).max() <= GTOL
     assert out["iters"].max() <= 20
+
+
+# Product-form configurations that no golden / sweep shape reaches (found by enumerating plan_init over a shape grid):
+# (nBatch, nz, nineq, neq, seed) -> (pf_global, pf_threads, setup_pf, setup_fast, pf2_ok, pf3_ok)
+PF_OFF_GOLDEN = {
+    "wide_nz_eq":     ((3, 181, 49, 8, 51),  (1, 256, 1, 0, 1, 1)),   # nz > 128: W / chol(Q) from L2 at ONE QP per SM, 256 threads
+    "wide_nz":        ((3, 235, 34, 0, 52),  (1, 256, 0, 0, 1, 1)),   # nz > 208: generic global-scratch setup writing the staircase
+    "wide_nz_small":  ((3, 230, 20, 4, 58),  (1, 256, 0, 0, 1, 1)),
+    "tall_resident":  ((3, 60, 130, 4, 54),  (0, 256, 1, 0, 0, 0)),   # order 144 > 128 with everything in shared memory
+    "tall_512_eq":    ((3, 124, 190, 8, 55), (1, 512, 1, 0, 0, 0)),   # 512-thread build with equality columns
+    "tall_512":       ((3, 100, 150, 0, 59), (1, 512, 1, 0, 0, 0)),
+    "wide_512":       ((3, 211, 130, 0, 56), (1, 512, 0, 0, 0, 0)),   # 512-thread solve after the generic setup
+    "mid_two_per_sm": ((3, 151, 100, 8, 57), (1, 256, 1, 0, 1, 0)),   # order 112: two per SM possible, three not
+    "nz_above_cta":   ((3, 300, 40, 0, 60),  (1, 256, 0, 0, 1, 1)),   # nz > threads per CTA (256 and 192): strided x passes
+    "nz_400_eq":      ((2, 400, 60, 8, 61),  (1, 256, 0, 0, 1, 0)),
+}
+
+
+@pytest.mark.parametrize("mode", ["latency", "throughput"])
+@pytest.mark.parametrize("name", sorted(PF_OFF_GOLDEN))
+def test_product_form_configurations_off_the_golden_shapes(name, mode, monkeypatch):
+    """Each configuration against the oracle (per-QP semantics) at a well-posed shape (a quarter to a half of the
+    constraints active), in latency mode and - where the shape has a several-per-SM variant - in throughput mode."""
+    from qpth_b200 import _lib, qp as qpmod
+    (B, nz, nineq, neq, seed), want = PF_OFF_GOLDEN[name]
+    plan = _lib.plan_for(nz, nineq, neq, two=(mode == "throughput"))
+    assert plan.pf == 1 and plan.tiny == 0, name
+    assert (plan.pf_global, plan.pf_threads, plan.setup_pf, plan.setup_fast, plan.pf2_ok, plan.pf3_ok) == want, name
+    if mode == "throughput" and not (plan.pf2_ok or plan.pf3_ok):
+        pytest.skip("one QP per SM only for this shape")
+    monkeypatch.setattr(qpmod, "MODE", mode)
+    pr = random_qp_batch(B, nz, nineq, neq, seed=seed)
+    out = _run(pr)
+    ref = orc.qp_solve(pr["Q"], pr["p"], pr["G"], pr["h"], pr["A"], pr["b"], pr["dl"], per_qp=True)
+    assert rel_rows(out["zhat"], ref["zhat"]).max() <= ZTOL
+    for g, r in zip(out["grads"], ref["grads"]):
+        if r is None:
+            assert g is None
+        else:
+            assert rel_rows(g, r, floor=1e-4).max() <= GTOL
+    assert out["iters"].max() <= 20
