@@ -1,55 +1,84 @@
-"""GPU parity of the kernel families the product-form kernels shadow at the golden shapes, and of orders beyond them.
+"""GPU parity of the kernel families the product-form kernels shadow at the golden shapes, of orders beyond them, and of
+product-form configurations no golden shape reaches.
 
 The default plan sends every golden case with an order of 8..256 that fits shared memory through the product-form
 kernels (qp_pf.cuh). What is left for the round-1 kernels in the shipped configuration is (a) tiny problems (one warp
 per QP; covered by the c1 / testpy cases of test_gpu_parity.py) and (b) problems whose factor does not fit shared
 memory at all - order neq_pad + nineq > 256, or a staircase + vectors above 227 KB - which run the GLOBAL-SCRATCH
-kernels (plan.smem_resident == 0, plan.pf == 0). This file pins (b) against the oracle, and re-runs the band / C4
-goldens with QPB200_PF=0 so that the generic shared-memory and global-scratch solve kernels keep a parity check at the
-shapes of the real reference's outputs too. (Named to sort after the other GPU files. Written after the round's GPU budget was spent: the test logic was dry-run here
-with oracle/kernel_model.py standing in for the CUDA path; its first run on hardware is the round-end run.)
+kernels (plan.smem_resident == 0, plan.pf == 0). This file pins (b) against the oracle, re-runs the band / C4 goldens
+with QPB200_PF=0 so that the generic shared-memory and global-scratch solve kernels keep a parity check at the shapes of
+the real reference's outputs too, and covers the product-form configurations found by enumerating plan_init over a
+shape grid (wide nz, orders above 128, the 512-thread build with equalities, nz above the CTA size).
+
+Written after the round's GPU budget was spent: the comparison logic was dry-run here with oracle/kernel_model.py
+standing in for the CUDA path, and the first run on hardware is the round-end one. For that reason the solves run in
+ONE child process (tests/gpu_child.py, jobs in tests/fallback_jobs.py) with a timeout: a fault or a hang in a
+configuration that has never run cannot take the rest of the GPU suite with it. (Named to sort after the other files.)
 """
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
 from oracle import pdipm_oracle as orc
 from oracle.cases import load_case
 from qpth_b200.problems import random_qp_batch
+from tests.fallback_jobs import BEYOND_SMEM, PF0_GOLDEN, PF_OFF_GOLDEN
 from tests.parity import check_against_golden, rel_rows, ZTOL, GTOL
-from tests.test_gpu_parity import _run, _report, EXPECTED_PATH
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD_TIMEOUT_S = 600
+# (fast, setup_fast, smem_resident) under QPB200_PF=0 (the table of test_gpu_parity.py)
+PF0_PATH = {"band_smem": (0, 0, 1), "band_smem_eq": (0, 0, 1), "band_setup": (1, 0, 1), "band_setup_eq": (1, 0, 1),
+            "c4": (0, 0, 0)}
 
 
-@pytest.mark.parametrize("name", ["band_smem", "band_smem_eq", "band_setup", "band_setup_eq", "c4"])
-def test_round1_kernel_families_match_golden(name, golden_dir, monkeypatch):
-    """QPB200_PF=0: generic shared-memory kernels (nineq > 104), fast solve + generic setup (nz > 104), and the
-    global-scratch kernels (C4, 200 x 200) against the real reference's outputs."""
+@pytest.fixture(scope="module")
+def child_results(tmp_path_factory):
+    out_dir = str(tmp_path_factory.mktemp("fallback_families"))
+    note = ""
+    try:
+        r = subprocess.run([sys.executable, "-m", "tests.gpu_child", out_dir], cwd=ROOT, timeout=CHILD_TIMEOUT_S,
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            note = "child exited with %d: %s" % (r.returncode, (r.stderr or "")[-2000:])
+    except subprocess.TimeoutExpired:
+        note = "child killed after %d s (a job hung)" % CHILD_TIMEOUT_S
+    return out_dir, note
+
+
+def _load(child_results, job):
+    out_dir, note = child_results
+    path = os.path.join(out_dir, job + ".npz")
+    if not os.path.exists(path):
+        err = os.path.join(out_dir, job + ".err")
+        why = open(err).read()[-3000:] if os.path.exists(err) else ("no result: " + (note or "job never ran"))
+        pytest.fail("%s: %s" % (job, why), pytrace=False)
+    d = np.load(path)
+    out = {k: d[k] for k in ("zhat", "lam", "slacks", "iters")}
+    out["nus"] = d["nus"] if "nus" in d else None
+    out["grads"] = tuple(d["grad%d" % i] if ("grad%d" % i) in d else None for i in range(6))
+    return out
+
+
+def _plan_with_env(env, *shape, **kw):
     from qpth_b200 import _lib
-    monkeypatch.setenv("QPB200_PF", "0")
-    prob, gold, full = load_case(name, golden_dir)
-    Qs, Gs, As = np.asarray(prob["Q"]), np.asarray(prob["G"]), np.asarray(prob["A"])
-    plan = _lib.plan_for(Qs.shape[-1], Gs.shape[-2], As.shape[-2] if As.size else 0)
-    assert plan.pf == 0 and (plan.fast, plan.setup_fast, plan.smem_resident) == EXPECTED_PATH[name], name
-    if name == "c4":
-        assert plan.solve_scratch_elems > 0 and plan.setup_scratch_elems > 0
-    out = _run(prob)
-    errs = check_against_golden(out, gold, full, what=name + "[pf0]", prob=prob)
-    _report(name + "[pf0]", errs)
+    saved = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return _lib.plan_for(*shape, **kw)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
-@pytest.mark.parametrize("cfg", [dict(nBatch=3, nz=120, nineq=260, neq=0, seed=41),
-                                 dict(nBatch=3, nz=260, nineq=300, neq=0, seed=43),
-                                 dict(nBatch=2, nz=300, nineq=300, neq=10, seed=44)])
-def test_orders_beyond_shared_memory_vs_oracle(cfg):
-    """Orders above 256 (no product-form kernel, nothing fits shared memory): the shipped plan is the global-scratch
-    family. z* and every gradient against the oracle (per-QP semantics); the shapes are well posed (110-150 active
-    constraints, so no gradient is vertex noise)."""
-    from qpth_b200 import _lib
-    plan = _lib.plan_for(cfg["nz"], cfg["nineq"], cfg["neq"])
-    assert (plan.tiny, plan.pf, plan.smem_resident) == (0, 0, 0) and plan.solve_scratch_elems > 0
-    pr = random_qp_batch(**cfg)
-    out = _run(pr)
+def _check_vs_oracle(out, pr):
     ref = orc.qp_solve(pr["Q"], pr["p"], pr["G"], pr["h"], pr["A"], pr["b"], pr["dl"], per_qp=True)
     assert rel_rows(out["zhat"], ref["zhat"]).max() <= ZTOL
     for g, r in zip(out["grads"], ref["grads"]):
@@ -60,42 +89,42 @@ def test_orders_beyond_shared_memory_vs_oracle(cfg):
     assert out["iters"].max() <= 20
 
 
-# Product-form configurations that no golden / sweep shape reaches (found by enumerating plan_init over a shape grid):
-# (nBatch, nz, nineq, neq, seed) -> (pf_global, pf_threads, setup_pf, setup_fast, pf2_ok, pf3_ok)
-PF_OFF_GOLDEN = {
-    "wide_nz_eq":     ((3, 181, 49, 8, 51),  (1, 256, 1, 0, 1, 1)),   # nz > 128: W / chol(Q) from L2 at ONE QP per SM, 256 threads
-    "wide_nz":        ((3, 235, 34, 0, 52),  (1, 256, 0, 0, 1, 1)),   # nz > 208: generic global-scratch setup writing the staircase
-    "wide_nz_small":  ((3, 230, 20, 4, 58),  (1, 256, 0, 0, 1, 1)),
-    "tall_resident":  ((3, 60, 130, 4, 54),  (0, 256, 1, 0, 0, 0)),   # order 144 > 128 with everything in shared memory
-    "tall_512_eq":    ((3, 124, 190, 8, 55), (1, 512, 1, 0, 0, 0)),   # 512-thread build with equality columns
-    "tall_512":       ((3, 100, 150, 0, 59), (1, 512, 1, 0, 0, 0)),
-    "wide_512":       ((3, 211, 130, 0, 56), (1, 512, 0, 0, 0, 0)),   # 512-thread solve after the generic setup
-    "mid_two_per_sm": ((3, 151, 100, 8, 57), (1, 256, 1, 0, 1, 0)),   # order 112: two per SM possible, three not
-    "nz_above_cta":   ((3, 300, 40, 0, 60),  (1, 256, 0, 0, 1, 1)),   # nz > threads per CTA (256 and 192): strided x passes
-    "nz_400_eq":      ((2, 400, 60, 8, 61),  (1, 256, 0, 0, 1, 0)),
-}
+@pytest.mark.parametrize("name", PF0_GOLDEN)
+def test_round1_kernel_families_match_golden(name, golden_dir, child_results):
+    """QPB200_PF=0: generic shared-memory kernels (nineq > 104), fast solve + generic setup (nz > 104), and the
+    global-scratch kernels (C4, 200 x 200) against the real reference's outputs."""
+    prob, gold, full = load_case(name, golden_dir)
+    Qs, Gs, As = np.asarray(prob["Q"]), np.asarray(prob["G"]), np.asarray(prob["A"])
+    plan = _plan_with_env({"QPB200_PF": "0"}, Qs.shape[-1], Gs.shape[-2], As.shape[-2] if As.size else 0)
+    assert plan.pf == 0 and (plan.fast, plan.setup_fast, plan.smem_resident) == PF0_PATH[name], name
+    if name == "c4":
+        assert plan.solve_scratch_elems > 0 and plan.setup_scratch_elems > 0
+    out = _load(child_results, "pf0_" + name)
+    check_against_golden(out, gold, full, what=name + "[pf0]", prob=prob)
+
+
+@pytest.mark.parametrize("name", sorted(BEYOND_SMEM))
+def test_orders_beyond_shared_memory_vs_oracle(name, child_results):
+    """Orders above 256 (no product-form kernel, nothing fits shared memory): the shipped plan is the global-scratch
+    family. z* and every gradient against the oracle (per-QP semantics); the shapes are well posed (110-150 active
+    constraints, so no gradient is vertex noise)."""
+    from qpth_b200 import _lib
+    cfg = BEYOND_SMEM[name]
+    plan = _lib.plan_for(cfg["nz"], cfg["nineq"], cfg["neq"])
+    assert (plan.tiny, plan.pf, plan.smem_resident) == (0, 0, 0) and plan.solve_scratch_elems > 0
+    _check_vs_oracle(_load(child_results, "big_" + name), random_qp_batch(**cfg))
 
 
 @pytest.mark.parametrize("mode", ["latency", "throughput"])
 @pytest.mark.parametrize("name", sorted(PF_OFF_GOLDEN))
-def test_product_form_configurations_off_the_golden_shapes(name, mode, monkeypatch):
+def test_product_form_configurations_off_the_golden_shapes(name, mode, child_results):
     """Each configuration against the oracle (per-QP semantics) at a well-posed shape (a quarter to a half of the
     constraints active), in latency mode and - where the shape has a several-per-SM variant - in throughput mode."""
-    from qpth_b200 import _lib, qp as qpmod
+    from qpth_b200 import _lib
     (B, nz, nineq, neq, seed), want = PF_OFF_GOLDEN[name]
     plan = _lib.plan_for(nz, nineq, neq, two=(mode == "throughput"))
     assert plan.pf == 1 and plan.tiny == 0, name
     assert (plan.pf_global, plan.pf_threads, plan.setup_pf, plan.setup_fast, plan.pf2_ok, plan.pf3_ok) == want, name
     if mode == "throughput" and not (plan.pf2_ok or plan.pf3_ok):
         pytest.skip("one QP per SM only for this shape")
-    monkeypatch.setattr(qpmod, "MODE", mode)
-    pr = random_qp_batch(B, nz, nineq, neq, seed=seed)
-    out = _run(pr)
-    ref = orc.qp_solve(pr["Q"], pr["p"], pr["G"], pr["h"], pr["A"], pr["b"], pr["dl"], per_qp=True)
-    assert rel_rows(out["zhat"], ref["zhat"]).max() <= ZTOL
-    for g, r in zip(out["grads"], ref["grads"]):
-        if r is None:
-            assert g is None
-        else:
-            assert rel_rows(g, r, floor=1e-4).max() <= GTOL
-    assert out["iters"].max() <= 20
+    _check_vs_oracle(_load(child_results, "pf_%s_%s" % (name, mode)), random_qp_batch(B, nz, nineq, neq, seed=seed))
