@@ -30,7 +30,7 @@ from tests.parity import check_against_golden, rel_rows, ZTOL, GTOL
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CHILD_TIMEOUT_S = 600
+CHILD_TIMEOUT_S = 240
 # (fast, setup_fast, smem_resident) under QPB200_PF=0 (the table of test_gpu_parity.py)
 PF0_PATH = {"band_smem": (0, 0, 1), "band_smem_eq": (0, 0, 1), "band_setup": (1, 0, 1), "band_setup_eq": (1, 0, 1),
             "c4": (0, 0, 0)}
