@@ -291,8 +291,12 @@ def QPFunction(eps=1e-12, verbose=0, notImprovedLim=3, maxIter=20, solver=QPSolv
                 grads.append(None if g is None else g.to(device=X.device, dtype=X.dtype))
             return tuple(grads)
 
-    def apply(*args):
-        return QPFunctionFn.apply(*args)
+    def apply(Q_, p_, G_, h_, A_, b_):
+        if G_.nelement() == 0 and h_.nelement() == 0 and A_.nelement() > 0:
+            # equality-constrained QP: an extension (the reference cannot run nineq == 0); one KKT solve, eqonly.py
+            from .eqonly import solve_equality_qp
+            return solve_equality_qp(Q_, p_, A_, b_, check_Q_spd)
+        return QPFunctionFn.apply(Q_, p_, G_, h_, A_, b_)
 
     # diagnostics the reference keeps on ctx (nus / lams / slacks) plus per-QP iteration counts
     apply.last_solve = lambda: _last[0]

@@ -31,6 +31,23 @@ PF_OFF_GOLDEN = {
 }
 
 
+# equality-only QPs (nineq == 0: qpth_b200/eqonly.py, an extension of the reference's surface) against the closed form
+EQ_ONLY = {
+    "eq_tiny": dict(B=5, nz=12, neq=5, shared=False, seed=71),          # one warp per system
+    "eq_c2_sized": dict(B=4, nz=100, neq=30, shared=False, seed=72),    # product-form kernels
+    "eq_shared": dict(B=6, nz=40, neq=10, shared=True, seed=73),        # un-batched Q and A: gradients are batch means
+}
+
+
+def eq_only_problem(B, nz, neq, shared, seed):
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    L = rs.randn(nz, nz) if shared else rs.randn(B, nz, nz)
+    Q = L @ np.swapaxes(L, -1, -2) + 0.1 * np.eye(nz)
+    A = rs.randn(neq, nz) if shared else rs.randn(B, neq, nz)
+    return dict(Q=Q, p=rs.randn(B, nz), A=A, b=rs.randn(B, neq), dl=rs.randn(B, nz))
+
+
 def jobs():
     """[(job name, kind, payload, env, mode)] in execution order."""
     out = []
@@ -42,4 +59,6 @@ def jobs():
         cfg = dict(nBatch=B, nz=nz, nineq=nineq, neq=neq, seed=seed)
         for mode in ("latency", "throughput"):
             out.append(("pf_%s_%s" % (name, mode), "random", cfg, {}, mode))
+    for name, cfg in EQ_ONLY.items():
+        out.append((name, "eq_only", cfg, {}, None))
     return out

@@ -25,7 +25,7 @@ import pytest
 from oracle import pdipm_oracle as orc
 from oracle.cases import load_case
 from qpth_b200.problems import random_qp_batch
-from tests.fallback_jobs import BEYOND_SMEM, PF0_GOLDEN, PF_OFF_GOLDEN
+from tests.fallback_jobs import BEYOND_SMEM, EQ_ONLY, PF0_GOLDEN, PF_OFF_GOLDEN, eq_only_problem
 from tests.parity import check_against_golden, rel_rows, ZTOL, GTOL
 
 pytestmark = pytest.mark.gpu
@@ -58,7 +58,7 @@ def _load(child_results, job):
         why = open(err).read()[-3000:] if os.path.exists(err) else ("no result: " + (note or "job never ran"))
         pytest.fail("%s: %s" % (job, why), pytrace=False)
     d = np.load(path)
-    out = {k: d[k] for k in ("zhat", "lam", "slacks", "iters")}
+    out = {k: d[k] for k in ("zhat", "lam", "slacks", "iters") if k in d}
     out["nus"] = d["nus"] if "nus" in d else None
     out["grads"] = tuple(d["grad%d" % i] if ("grad%d" % i) in d else None for i in range(6))
     return out
@@ -128,3 +128,26 @@ def test_product_form_configurations_off_the_golden_shapes(name, mode, child_res
     if mode == "throughput" and not (plan.pf2_ok or plan.pf3_ok):
         pytest.skip("one QP per SM only for this shape")
     _check_vs_oracle(_load(child_results, "pf_%s_%s" % (name, mode)), random_qp_batch(B, nz, nineq, neq, seed=seed))
+
+
+@pytest.mark.parametrize("name", sorted(EQ_ONLY))
+def test_equality_only_qp_vs_closed_form(name, child_results):
+    """nineq == 0 (qpth_b200/eqonly.py: two stand-alone KKT solves on the kernels): z* and the gradients against torch
+    autograd through the dense KKT solution on the CPU, with the reference's conventions (symmetrised dQ, batch mean for
+    un-batched inputs)."""
+    import torch
+    cfg = EQ_ONLY[name]
+    pr = eq_only_problem(**cfg)
+    B, nz, neq, shared = cfg["B"], cfg["nz"], cfg["neq"], cfg["shared"]
+    Q, p, A, b = (torch.tensor(pr[k], requires_grad=True) for k in ("Q", "p", "A", "b"))
+    Qb = Q.expand(B, nz, nz) if shared else Q
+    Ab = A.expand(B, neq, nz) if shared else A
+    K = torch.cat([torch.cat([Qb, Ab.transpose(1, 2)], 2), torch.cat([Ab, torch.zeros(B, neq, neq, dtype=Q.dtype)], 2)], 1)
+    z = torch.linalg.solve(K, torch.cat([-p, b], 1).unsqueeze(-1)).squeeze(-1)[:, :nz]
+    z.backward(torch.tensor(pr["dl"]))
+    out = _load(child_results, name)
+    assert rel_rows(out["zhat"], z.detach().numpy()).max() <= ZTOL
+    ref = (0.5 * (Q.grad + Q.grad.transpose(-1, -2)) / (B if shared else 1), p.grad, A.grad / (B if shared else 1), b.grad)
+    for g, r in zip(out["grads"][:4], ref):
+        assert g.shape == tuple(r.shape)
+        assert rel_rows(g, r.numpy(), floor=1e-4).max() <= GTOL
